@@ -1,0 +1,132 @@
+/*
+ * mcalf_b200.h -- C ABI of the B200-native MC-ALF likelihood hot path (libmcalf_b200.so).
+ *
+ * The reference (matteofox/MC-ALF) is pure Python and has no FFI of its own; the boundary this
+ * library sits behind is the set of bound methods of `als_fitter` that the nested samplers call
+ * (mcalf/routines/hires_fitter.py).  Each entry point below names the reference code it replaces.
+ * INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
+ * MCALF_E_* code, with a thread-local message available from mcalf_last_error().  The caller owns
+ * every in/out buffer.  A context is bound to one CUDA device and one in-flight call at a time.
+ * There is no CPU fallback: without a usable CUDA device mcalf_create() fails.
+ */
+#ifndef MCALF_B200_H
+#define MCALF_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCALF_ABI_VERSION 1
+
+/* error codes */
+#define MCALF_OK 0
+#define MCALF_E_INVALID (-1)   /* bad argument / inconsistent problem description            */
+#define MCALF_E_CUDA (-2)      /* CUDA runtime error (message carries cudaGetErrorString)     */
+#define MCALF_E_NODEVICE (-3)  /* no CUDA device: this library never computes on the host     */
+#define MCALF_E_RESOURCE (-4)  /* problem does not fit the kernel's shared-memory/line limits */
+
+/* flags for the batch calls (bitwise or) */
+#define MCALF_F_UNIT_CUBE 0x01  /* params are unit-cube draws: apply _scale_cube_pc first (hires_fitter.py:202-209) */
+#define MCALF_F_ON_DEVICE 0x02  /* params and outputs are device pointers on the context's device                */
+#define MCALF_F_FP64 0x04       /* use the fp64 check kernel (trapezoid-rule Faddeeva, ~1e-13)                   */
+#define MCALF_F_TARGONLY 0x08   /* skip filler lines: reconstruct_spec(p, targonly=True) (hires_fitter.py:437)   */
+#define MCALF_F_ONECOMP 0x10    /* params rows are [specres, continuum, N, z, b]: reconstruct_onecomp (:379-392) */
+#define MCALF_F_ONECOMP_FILL 0x20 /* as ONECOMP but with the filler line: reconstruct_onecomp_fill (:394-406)    */
+#define MCALF_F_NO_TRUNC 0x40   /* with UNIT_CUBE: _scale_cube_mn semantics, no int() on the ncomp slot (:211-216) */
+#define MCALF_F_FLUX_F64 0x80   /* mcalf_model_batch: flux_out is double[B*npix] instead of float[B*npix]        */
+
+/*
+ * Everything als_fitter.__init__ (hires_fitter.py:32-200) leaves behind that the likelihood reads.
+ * All arrays are host pointers, copied by mcalf_create().
+ */
+typedef struct mcalf_problem {
+    int32_t abi_version;      /* MCALF_ABI_VERSION */
+    int32_t npix;             /* pixels after the wavefit mask, windows concatenated (:75-82) */
+    const double *wave;       /* obj_wl  [npix], Angstrom                                      */
+    const double *flux;       /* obj     [npix] (NaN allowed: pixel dropped, nansum :294)      */
+    const double *err;        /* obj_noise [npix] (0 / NaN allowed: pixel dropped)             */
+    double velstep;           /* km/s per pixel, sigma-clipped median (:84-87)                 */
+    int32_t nlines;           /* numlines (:91)                                                */
+    const double *line_wrest; /* [nlines] Angstrom (:104-113)                                  */
+    const double *line_f;     /* [nlines] oscillator strengths                                 */
+    const double *line_gamma; /* [nlines] damping constants, 1/s                               */
+    double fill_wrest, fill_f, fill_gamma; /* linefill (:120-121): wrest = 250 A               */
+    int32_t ncompmax;         /* ncomp[1] (:48)                                                */
+    int32_t nfill;            /* (:44)                                                         */
+    int32_t free_specres;     /* len(specres) > 1 (:59-62)                                     */
+    int32_t free_cont;        /* len(contval) > 1 (:54-57)                                     */
+    double fixed_specres;     /* max(specres) when not free (:417)                             */
+    double fixed_cont;        /* contval[0] when not free (:425)                               */
+    int32_t ndim;             /* startind + 1 + 3*(ncompmax+nfill) (:200)                      */
+    int32_t asymmlike;        /* Asymmlike (:296)                                              */
+    const double *bounds_lo;  /* [ndim] min(bounds[i]) (:184-198)                              */
+    const double *bounds_hi;  /* [ndim] max(bounds[i])                                         */
+    double asym_thresh5;      /* gauss_cdf[2] + gracenum (:300)                                */
+    double asym_thresh4;      /* gauss_cdf[1] + gracenum (:302)                                */
+    double max_specres;       /* largest specres any call may carry; sizes the LSF halo (0: from bounds/fixed) */
+} mcalf_problem_t;
+
+typedef struct mcalf_ctx mcalf_ctx;
+
+/* counters accumulated over the calls of one context (reset with mcalf_reset_stats) */
+typedef struct mcalf_stats {
+    uint64_t kernel_launches;  /* CUDA kernels this library launched                          */
+    uint64_t samples;          /* parameter vectors evaluated                                 */
+    uint64_t evals_total;      /* (line, pixel) Voigt evaluations the reference would perform */
+    uint64_t evals_far;        /* ... served by the one-FMA far-wing form                     */
+    uint64_t evals_near;       /* ... served by the two-float near form                       */
+    uint64_t evals_core;       /* ... of the near ones re-done by the line-core path          */
+    uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound           */
+    uint64_t samples_fp64_fallback; /* samples re-routed to the fp64 kernel (a > a_max etc.)  */
+    double last_kernel_ms;     /* device time of the last batch call's main kernel (CUDA events) */
+} mcalf_stats_t;
+
+/* Build a context on CUDA device `device` (replaces als_fitter.__init__ state, :65-200). */
+int mcalf_create(const mcalf_problem_t *problem, int device, mcalf_ctx **out);
+void mcalf_destroy(mcalf_ctx *ctx);
+
+/*
+ * logL for B parameter vectors (row b at params + b*ld): replaces lnlhood_worker (:287-328) =
+ * reconstruct_spec (:409-449) -> voigt_model/voigt_tau (:331-377) -> convolve_model (:452-464) ->
+ * -0.5*nansum(...).  chi2_out may be NULL (else: chi2(p), :236-248).  stream: cudaStream_t or NULL.
+ * With host pointers the call stages through pinned memory and returns after the results landed;
+ * with MCALF_F_ON_DEVICE it only enqueues work on `stream`.
+ */
+int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
+                        void *stream, double *logl_out, double *chi2_out);
+
+/* Model flux for B parameter vectors, [B, npix] row-major: replaces reconstruct_spec (:409-449),
+ * reconstruct_onecomp (:379-392) and reconstruct_onecomp_fill (:394-406) via flags. */
+int mcalf_model_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
+                      void *stream, void *flux_out);
+
+/* Unit cube -> physical parameters for B rows: replaces _scale_cube_pc (:202-209), or
+ * _scale_cube_mn (:211-216) with MCALF_F_NO_TRUNC. */
+int mcalf_prior_transform_batch(mcalf_ctx *ctx, const double *cube, int64_t B, int64_t ld, uint32_t flags,
+                                void *stream, double *theta_out);
+
+/* Re w(u + i a) element-wise with the kernels' own device code (fp32 fast path: mode 0,
+ * fp64 check path: mode 1); for unit tests against scipy.special.wofz (:365). Host pointers. */
+int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_t n, double *h_out);
+
+int mcalf_get_stats(mcalf_ctx *ctx, mcalf_stats_t *out);
+int mcalf_reset_stats(mcalf_ctx *ctx);
+/* cull_eps: lines whose optical depth over a 256-pixel segment is provably below this are skipped
+ * (0 disables; default 0).  a_max: damping parameters above it route the sample to the fp64 kernel. */
+int mcalf_set_option(mcalf_ctx *ctx, const char *name, double value);
+
+/* pinned host buffers for callers that want the fast host path */
+int mcalf_host_alloc(void **ptr, uint64_t bytes);
+int mcalf_host_free(void *ptr);
+
+const char *mcalf_last_error(void);
+int mcalf_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCALF_B200_H */

@@ -1,0 +1,258 @@
+// voigt_math.cuh -- the arithmetic of the MC-ALF likelihood hot path, written once for device and
+// host.  The host build exists only so tests/ can exercise these exact functions without a GPU
+// (tests/host_emul); the product never computes on the host.
+//
+// Reference being replaced: als_fitter.voigt_tau (mcalf/routines/hires_fitter.py:331-367), whose
+// kernel is  tau = 0.014971475 * N * f * Re w(u + i a) / dnu  with w from scipy.special.wofz.
+//
+//   fp32 fast path   H(a,u) = Re w(u+ia) split at s = u^2 + a^2 = S_CUT (= 36):
+//       wing  (s >= S_CUT):  H = (a/sqrt pi) * q * P(q),  q = 1/s, P a degree-4 polynomial
+//                            (1 MUFU.RCP + 6 FMA-pipe ops, relative error 2e-8 + rounding)
+//       core  (s <  S_CUT):  Taylor series in a about the Gaussian (Harris 1948):
+//                            H = G0 (1 + a^2 (1-2x)) + a (G1 (1 + a^2 (1 - 2x/3)) + 2 a^2/(3 sqrt pi)),
+//                            x = u^2, G0 = exp(-x) from a two-float x, G1 = H1(u) from a Taylor table.
+//                            Valid for a <= A_MAX_FAST; larger a is routed to the fp64 path.
+//   fp64 check path  trapezoid rule with pole correction on one of two staggered grids
+//                    (Hunter & Regan 1972), asymptotic series for s > 100; ~1e-13 relative.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define MCALF_HD __host__ __device__ __forceinline__
+#else
+#define MCALF_HD inline
+#endif
+
+#include "voigt_tables.inc"
+
+namespace mcalf {
+
+constexpr double C_KMS = 2.9979245e5;        // hires_fitter.py:65
+constexpr double TAU_CONST = 0.014971475;    // hires_fitter.py:364
+constexpr double FWHM_TO_SIGMA = 2.354820;   // hires_fitter.py:454
+constexpr double TRUNC_SIGMAS = 3.0348;      // hires_fitter.py:458
+constexpr double PI_D = 3.14159265358979323846;
+constexpr double SQRTPI_D = 1.77245385090551602730;
+constexpr float S_CUT = MCALF_S_CUT;
+constexpr double A_MAX_FAST = 0.02;          // beyond this the a^4 term of the core series matters
+
+struct G1Row { float c0, c1, c2, c3; };
+
+#if defined(__CUDACC__)
+static __device__ const G1Row g1_tab_dev[MCALF_G1_N] = { MCALF_G1_ROWS };
+#endif
+static const G1Row g1_tab_host[MCALF_G1_N] = { MCALF_G1_ROWS };
+
+MCALF_HD float fma32(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
+
+MCALF_HD float rcp32(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// q*P(q) with q = 1/s: the wing shape.  Multiply by c1 = kappa*a/sqrt(pi) to get tau.
+MCALF_HD float wing_qp(float s) {
+    const float w[5] = MCALF_WING_P;
+    float q = rcp32(s);
+    float p = fma32(w[4], q, w[3]);
+    p = fma32(p, q, w[2]);
+    p = fma32(p, q, w[1]);
+    p = fma32(p, q, w[0]);
+    return p * q;
+}
+
+// exp(-(x + xlo)) for x >= 0, |xlo| << 1: Cody-Waite reduction, degree-7 polynomial, exact 2^-n scale.
+MCALF_HD float exp_neg32(float x, float xlo) {
+    const float c[8] = MCALF_EXPM_C;
+    x = fminf(x, 88.0f);
+    float n = rintf(x * 1.44269504088896341f);
+    float r = fma32(n, -0.693145751953125f, x);
+    r = fma32(n, -1.42860676533018702e-06f, r);
+    r += xlo;
+    float p = fma32(c[7], r, c[6]);
+    p = fma32(p, r, c[5]);
+    p = fma32(p, r, c[4]);
+    p = fma32(p, r, c[3]);
+    p = fma32(p, r, c[2]);
+    p = fma32(p, r, c[1]);
+    p = fma32(p, r, c[0]);
+    int e = 127 - (int)n;               // n in [0,127]
+    union { int32_t i; float f; } sc;
+    sc.i = e << 23;
+    return p * sc.f;
+}
+
+MCALF_HD G1Row g1_row(int j) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4 *>(g1_tab_dev) + j);
+    G1Row r; r.c0 = v.x; r.c1 = v.y; r.c2 = v.z; r.c3 = v.w;
+    return r;
+#else
+    return g1_tab_host[j];
+#endif
+}
+
+// Line-core H(a,u) for u given as a two-float (uh + ul), s = u^2+a^2 < S_CUT, a <= A_MAX_FAST.
+MCALF_HD float core_h32(float a, float a2, float uh, float ul) {
+    float x = uh * uh;
+    float xlo = fma32(uh, uh, -x) + 2.0f * uh * ul;
+    float g0 = exp_neg32(x, xlo);
+    float au = fabsf(uh);
+    float sl = (uh < 0.0f) ? -ul : ul;
+    float fj = rintf(au * (float)MCALF_G1_INV_H);
+    int j = (int)fj;
+    j = j < MCALF_G1_N - 1 ? j : MCALF_G1_N - 1;
+    float d = fma32(fj, -1.0f / (float)MCALF_G1_INV_H, au) + sl;
+    G1Row t = g1_row(j);
+    float g1 = fma32(fma32(fma32(t.c3, d, t.c2), d, t.c1), d, t.c0);
+    float k0 = fma32(a2, fma32(-2.0f, x, 1.0f), 1.0f);
+    float k1 = fma32(a2, fma32(-0.666666687f, x, 1.0f), 1.0f);
+    float inner = fma32(g1, k1, a2 * 0.376126389f);
+    return fma32(g0, k0, a * inner);
+}
+
+// Convenience scalar form of the fast path (unit tests, mcalf_voigt_h): u, a as floats.
+MCALF_HD float voigt_h32(float a, float u) {
+    float a2 = a * a;
+    float s = fma32(u, u, a2);
+    if (s < S_CUT) return core_h32(a, a2, u, 0.0f);
+    return a * 0.564189584f * wing_qp(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp64 check path
+// ---------------------------------------------------------------------------------------------
+MCALF_HD double voigt_h64(double a, double u) {
+    const double e0[MCALF_TRAP_N] = MCALF_TRAP_E0;
+    const double e1[MCALF_TRAP_N] = MCALF_TRAP_E1;
+    const double h = MCALF_TRAP_H;
+    u = fabs(u);
+    const double a2 = a * a;
+    const double s = u * u + a2;
+    if (s > 100.0 || a > 5.0) {
+        // Re[(i/sqrt pi)/z * (1 + sum_k (2k-1)!!/(2 z^2)^k)], z = u + i a, Horner from k = 12
+        const double inv = 1.0 / s;
+        const double zr = u * inv, zi = -a * inv;             // 1/z
+        const double wr = zr * zr - zi * zi, wi = 2.0 * zr * zi;  // 1/z^2
+        double ar = 0.0, ai = 0.0;
+        for (int k = 12; k >= 1; --k) {
+            const double c = 0.5 * (2 * k - 1);
+            const double tr = (ar + 1.0) * c, ti = ai * c;
+            ar = tr * wr - ti * wi;
+            ai = tr * wi + ti * wr;
+        }
+        // (i/z)(1+acc): i*(zr + i zi) = -zi + i zr
+        const double br = -zi, bi = zr;
+        return (br * (1.0 + ar) - bi * ai) / SQRTPI_D;
+    }
+    const double f = u / h - floor(u / h);
+    const bool half = fabs(f - 0.5) > 0.25;   // u close to an integer node: use the staggered grid
+    double sum = 0.0;
+    if (!half) {
+        sum = e0[0] / (u * u + a2);
+        for (int k = 1; k < MCALF_TRAP_N; ++k) {
+            const double t = k * h;
+            sum += e0[k] * (1.0 / ((u - t) * (u - t) + a2) + 1.0 / ((u + t) * (u + t) + a2));
+        }
+    } else {
+        for (int k = 0; k < MCALF_TRAP_N; ++k) {
+            const double t = (k + 0.5) * h;
+            sum += e1[k] * (1.0 / ((u - t) * (u - t) + a2) + 1.0 / ((u + t) * (u + t) + a2));
+        }
+    }
+    double res = h / PI_D * a * sum;
+    // pole correction Re[2 exp(-z^2) / (1 - sg exp(-2 pi i z / h))]
+    const double sg = half ? -1.0 : 1.0;
+    const double ex = exp(a2 - u * u);
+    const double c2 = cos(2.0 * u * a), s2 = sin(2.0 * u * a);
+    const double E = exp(2.0 * PI_D * a / h);
+    const double th = 2.0 * PI_D * (u / h);
+    const double dr = 1.0 - sg * E * cos(th), di = sg * E * sin(th);
+    res += 2.0 * ex * (c2 * dr - s2 * di) / (dr * dr + di * di);
+    return res;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-line set-up (fp64, once per (sample, line)): voigt_tau's scalars in the well-conditioned form
+//   u = A (rho - rho_c),  rho = lam_ref/lambda,  rho_c = lam_ref/(wrest (1+z)),  A = (c/b) wrest (1+z)/lam_ref
+//   tau = kappa H(a,u),  kappa = 0.014971475 10^logN f wrest_cm / b_cms,  a = gamma wrest_cm / (4 pi b_cms)
+// (algebraically identical to hires_fitter.py:355-365).
+// ---------------------------------------------------------------------------------------------
+struct Line64 {
+    double A, rc, kappa, a;
+};
+
+struct Line32 {
+    float A_hi, A_lo, rc_hi, rc_lo;   // two-float A and rho_c
+    float U0, c1, a, a2;              // U0 = -A*rho_c; c1 = kappa*a/sqrt(pi)
+    float kappa, d_near, d_cull, c1w; // c1w = c1 * wing_qp(S_CUT) (what the clamped wing added)
+};
+
+MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, double f, double gamma,
+                             double lam_ref) {
+    Line64 L;
+    const double lamc = wrest * (1.0 + z);
+    const double wrest_cm = wrest * 1e-8, b_cms = b_kms * 1e5;
+    L.A = (C_KMS / b_kms) * (lamc / lam_ref);
+    L.rc = lam_ref / lamc;
+    L.kappa = TAU_CONST * pow(10.0, logN) * f * wrest_cm / b_cms;
+    L.a = gamma * wrest_cm / (4.0 * PI_D * b_cms);
+    return L;
+}
+
+MCALF_HD void split2(double v, float &hi, float &lo) {
+    hi = (float)v;
+    lo = (float)(v - (double)hi);
+}
+
+// eps_far: optical-depth error allowed to the one-FMA far form; eps_cull: optical depth below
+// which a line is skipped on a segment (0 = never).
+MCALF_HD Line32 line_setup32(const Line64 &L, double eps_far, double eps_cull) {
+    Line32 o;
+    split2(L.A, o.A_hi, o.A_lo);
+    split2(L.rc, o.rc_hi, o.rc_lo);
+    o.U0 = (float)(-L.A * L.rc);
+    const double c1 = L.kappa * L.a / SQRTPI_D;
+    o.c1 = (float)c1;
+    o.a = (float)L.a;
+    o.a2 = (float)(L.a * L.a);
+    o.kappa = (float)L.kappa;
+    const float wcut = 0.0288810f;  // ~ q P(q) at s = S_CUT, recomputed exactly below
+    (void)wcut;
+    o.c1w = o.c1 * wing_qp(S_CUT);
+    // far form  u = fma(A_hi, rho_hi, U0): |du| <= 3 * 2^-24 * |A rho|  (rho_hi, product, U0 roundings)
+    // => |dtau| <= 2 c1 |du| / u^3 * 1.05.  Need u >= u_far for |dtau| <= eps_far; never inside the core.
+    const double du = 3.0 * 5.97e-8 * fabs(L.A) * 1.001 * (L.rc > 1.0 ? L.rc : 1.0);
+    double u_far = cbrt(2.1 * c1 * du / eps_far);
+    const double u_core = sqrt((double)S_CUT) * 1.02 + 2.0 * du;
+    if (!(u_far > u_core)) u_far = u_core;
+    o.d_near = (float)(u_far / fabs(L.A) * 1.0001);
+    if (eps_cull > 0.0) {
+        double u_cull = sqrt(1.05 * c1 / eps_cull);
+        if (!(u_cull > u_far)) u_cull = u_far;
+        o.d_cull = (float)(u_cull / fabs(L.A) * 1.0001);
+    } else {
+        o.d_cull = 3.0e38f;
+    }
+    return o;
+}
+
+// LSF geometry (hires_fitter.py:452-459): sigma in pixels and half-width n = ceil(3.0348 sigma).
+MCALF_HD void lsf_geometry(double fwhm, double velstep, double &sigma_px, int &n) {
+    sigma_px = (fwhm / FWHM_TO_SIGMA) / velstep;
+    n = (int)ceil(TRUNC_SIGMAS * sigma_px);
+}
+
+}  // namespace mcalf
