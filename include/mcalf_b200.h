@@ -74,15 +74,16 @@ typedef struct mcalf_ctx mcalf_ctx;
 
 /* counters accumulated over the calls of one context (reset with mcalf_reset_stats) */
 typedef struct mcalf_stats {
-    uint64_t kernel_launches;  /* CUDA kernels this library launched                          */
-    uint64_t samples;          /* parameter vectors evaluated                                 */
-    uint64_t evals_total;      /* (line, pixel) Voigt evaluations the reference would perform */
-    uint64_t evals_far;        /* ... served by the one-FMA far-wing form                     */
-    uint64_t evals_near;       /* ... served by the two-float near form                       */
-    uint64_t evals_core;       /* ... of the near ones re-done by the line-core path          */
-    uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound           */
-    uint64_t samples_fp64_fallback; /* samples re-routed to the fp64 kernel (a > a_max etc.)  */
-    double last_kernel_ms;     /* device time of the last batch call's main kernel (CUDA events) */
+    uint64_t kernel_launches;  /* CUDA kernels this library launched                                    */
+    uint64_t samples;          /* parameter vectors evaluated                                           */
+    uint64_t samples_fp64;     /* ... of which by the fp64 kernel (MCALF_F_FP64, or re-routed: a > a_max) */
+    /* the next five only advance while option "collect_stats" is 1 (fp32 kernel)                       */
+    uint64_t evals_total;      /* (line, pixel) Voigt evaluations the reference would perform           */
+    uint64_t evals_wing;       /* ... in (line, chunk) pairs served by the wing-only form               */
+    uint64_t evals_mixed;      /* ... in pairs that may contain line-core pixels                        */
+    uint64_t evals_core;       /* ... of the mixed ones that took the line-core branch                  */
+    uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound                     */
+    double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events)            */
 } mcalf_stats_t;
 
 /* Build a context on CUDA device `device` (replaces als_fitter.__init__ state, :65-200). */
@@ -115,9 +116,22 @@ int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_
 
 int mcalf_get_stats(mcalf_ctx *ctx, mcalf_stats_t *out);
 int mcalf_reset_stats(mcalf_ctx *ctx);
-/* cull_eps: lines whose optical depth over a 256-pixel segment is provably below this are skipped
- * (0 disables; default 0).  a_max: damping parameters above it route the sample to the fp64 kernel. */
+/* Options: "cull_eps"  (line, chunk) pairs whose optical depth is provably below it are skipped
+ *                      (default 0 = never: the reference never skips);
+ *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default and
+ *                      upper limit 0.02: the validity range of the fp32 line-core series);
+ *          "collect_stats" 0/1; "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);
+ *          "ctas_per_sm" persistent CTAs per SM (0 = what the occupancy calculator allows);
+ *          "slice" samples per pipelined slice of the host-pointer path. */
 int mcalf_set_option(mcalf_ctx *ctx, const char *name, double value);
+int mcalf_get_option(mcalf_ctx *ctx, const char *name, double *value);
+
+/* Geometry the context chose: npix, number of chunks, CTA size, CTAs per SM, SM count, dynamic shared
+ * memory per CTA, LSF halo, maximum line count.  out[8]. */
+int mcalf_get_geometry(mcalf_ctx *ctx, int64_t *out);
+
+/* Measured FP32 peak of `device`: an FFMA-only kernel, CUDA-event timed; returns TFLOP/s (FMA = 2). */
+int mcalf_ffma_peak(int device, double *tflops_out);
 
 /* pinned host buffers for callers that want the fast host path */
 int mcalf_host_alloc(void **ptr, uint64_t bytes);

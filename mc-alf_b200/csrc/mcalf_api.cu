@@ -1,0 +1,615 @@
+// mcalf_api.cu -- the C ABI of libmcalf_b200.so (include/mcalf_b200.h): context construction from
+// the als_fitter state, batch entry points, the pipelined host-pointer path.  No computation happens
+// on the host here beyond the one-off per-pixel set-up of mcalf_create (the analogue of
+// als_fitter.__init__, hires_fitter.py:65-200); without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "mcalf_device.h"
+
+using namespace mcalf;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail(MCALF_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int NBUF = 2;
+constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
+constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
+constexpr double A_MAX_LIMIT = 0.02;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr, k0 = nullptr, k1 = nullptr;
+    double *h_params = nullptr, *d_params = nullptr;   // pinned / device, slice * ld_cap doubles
+    double *h_out = nullptr, *d_out = nullptr;         // 2 * slice doubles (logL, chi2)
+    void *h_flux = nullptr, *d_flux = nullptr;
+    size_t flux_cap = 0, params_cap = 0, out_cap = 0;
+    unsigned int *counters = nullptr;                  // [2]: work counter, fallback count
+    int *fallback = nullptr;                           // [fallback_cap]
+    size_t fallback_cap = 0;
+};
+
+}  // namespace
+
+struct mcalf_ctx {
+    int device = 0, sm_count = 0;
+    DevProblem P{};
+    std::vector<void *> allocs;
+    Slot slot[NBUF];
+    unsigned long long *d_stats = nullptr;
+    int threads = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0;
+    size_t smem_fast = 0, smem_fp64 = 0;
+    long long slice = 16384;
+    int collect_stats = 0;
+    uint64_t kernel_launches = 0, samples = 0, samples_fp64 = 0;
+    int last_slot = -1;
+};
+
+namespace {
+
+template <typename T>
+int upload(mcalf_ctx *c, const std::vector<T> &v, const T **out) {
+    void *d = nullptr;
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CU(cudaMalloc(&d, bytes));
+    c->allocs.push_back(d);
+    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T *)d;
+    return MCALF_OK;
+}
+
+int choose_launch(mcalf_ctx *c) {
+    const DevProblem &P = c->P;
+    int nwarps = c->threads_opt > 0 ? c->threads_opt / 32 : std::min(std::max(P.nchunks, 2), 8);
+    if (nwarps < 1) nwarps = 1;
+    if (nwarps > 32) nwarps = 32;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, c->device));
+    size_t smem = fast_smem_bytes(P, nwarps);
+    while (smem > (size_t)prop.sharedMemPerBlockOptin && nwarps > 1) {
+        nwarps = (nwarps + 1) / 2;
+        smem = fast_smem_bytes(P, nwarps);
+    }
+    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(MCALF_E_RESOURCE, "problem needs %zu B of shared memory per CTA (limit %zu): too many pixels/lines", smem,
+                    (size_t)prop.sharedMemPerBlockOptin);
+    c->smem_fp64 = fp64_smem_bytes(P);
+    if (c->smem_fp64 > (size_t)prop.sharedMemPerBlockOptin)
+        return fail(MCALF_E_RESOURCE, "fp64 kernel needs %zu B of shared memory per CTA (limit %zu)", c->smem_fp64,
+                    (size_t)prop.sharedMemPerBlockOptin);
+    c->threads = nwarps * 32;
+    c->smem_fast = smem;
+    CU(configure_kernels(c->smem_fast, c->smem_fp64));
+    int occ = 0;
+    CU(fast_occupancy(c->threads, c->smem_fast, &occ));
+    if (occ < 1) return fail(MCALF_E_RESOURCE, "fp32 kernel does not fit an SM (threads %d, smem %zu)", c->threads, smem);
+    c->ctas_per_sm = c->ctas_opt > 0 ? std::min(c->ctas_opt, occ) : occ;
+    return MCALF_OK;
+}
+
+int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_bytes, bool host_io) {
+    if (!s.stream) {
+        CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        CU(cudaEventCreate(&s.k0));
+        CU(cudaEventCreate(&s.k1));
+        CU(cudaMalloc((void **)&s.counters, 2 * sizeof(unsigned int)));
+    }
+    if ((size_t)n > s.fallback_cap) {
+        if (s.fallback) CU(cudaFree(s.fallback));
+        CU(cudaMalloc((void **)&s.fallback, sizeof(int) * (size_t)n));
+        s.fallback_cap = (size_t)n;
+    }
+    if (!host_io) return MCALF_OK;
+    const size_t pbytes = sizeof(double) * (size_t)n * (size_t)ld;
+    if (pbytes > s.params_cap) {
+        if (s.h_params) CU(cudaFreeHost(s.h_params));
+        if (s.d_params) CU(cudaFree(s.d_params));
+        CU(cudaMallocHost((void **)&s.h_params, pbytes));
+        CU(cudaMalloc((void **)&s.d_params, pbytes));
+        s.params_cap = pbytes;
+    }
+    const size_t obytes = sizeof(double) * 2 * (size_t)n;
+    if (obytes > s.out_cap) {
+        if (s.h_out) CU(cudaFreeHost(s.h_out));
+        if (s.d_out) CU(cudaFree(s.d_out));
+        CU(cudaMallocHost((void **)&s.h_out, obytes));
+        CU(cudaMalloc((void **)&s.d_out, obytes));
+        s.out_cap = obytes;
+    }
+    if (flux_bytes > s.flux_cap) {
+        if (s.h_flux) CU(cudaFreeHost(s.h_flux));
+        if (s.d_flux) CU(cudaFree(s.d_flux));
+        CU(cudaMallocHost(&s.h_flux, flux_bytes));
+        CU(cudaMalloc(&s.d_flux, flux_bytes));
+        s.flux_cap = flux_bytes;
+    }
+    return MCALF_OK;
+}
+
+// enqueue the kernels of one slice on `st`; all pointers are device pointers
+int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long long n, long long ld, uint32_t flags,
+            double *d_logl, double *d_chi2, void *d_flux) {
+    BatchArgs a{};
+    a.params = d_params;
+    a.B = n;
+    a.ld = ld;
+    a.flags = flags;
+    a.logl_out = d_logl;
+    a.chi2_out = d_chi2;
+    a.flux_out = d_flux;
+    a.work_counter = s.counters;
+    a.fallback_count = s.counters + 1;
+    a.fallback_list = s.fallback;
+    a.stats = c->collect_stats ? c->d_stats : nullptr;
+    CU(cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned int), st));
+    CU(cudaEventRecord(s.k0, st));
+    const int fp64_grid = (int)std::min<long long>(n, (long long)c->sm_count * 8);
+    if (flags & MCALF_F_FP64) {
+        CU(launch_fp64(c->P, a, nullptr, nullptr, fp64_grid, c->smem_fp64, st));
+        c->kernel_launches += 1;
+        c->samples_fp64 += (uint64_t)n;
+    } else {
+        const int grid = (int)std::min<long long>(n, (long long)c->sm_count * c->ctas_per_sm);
+        CU(launch_fast(c->P, a, grid, c->threads, c->smem_fast, st));
+        // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
+        // (exits at once when the list is empty)
+        const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);
+        CU(launch_fp64(c->P, a, s.fallback, s.counters + 1, fgrid, c->smem_fp64, st));
+        c->kernel_launches += 2;
+    }
+    CU(cudaEventRecord(s.k1, st));
+    c->samples += (uint64_t)n;
+    return MCALF_OK;
+}
+
+int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uint32_t flags, void *stream, double *logl,
+              double *chi2, void *flux) {
+    if (!c) return fail(MCALF_E_INVALID, "null context");
+    if (B < 0) return fail(MCALF_E_INVALID, "negative batch size");
+    if (B == 0) return MCALF_OK;
+    if (!params) return fail(MCALF_E_INVALID, "null params");
+    const int need = (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) ? 5 : c->P.ndim;
+    if (ld < need) return fail(MCALF_E_INVALID, "ld (%lld) smaller than the row length (%d)", ld, need);
+    if ((flags & MCALF_F_ONECOMP) && (flags & MCALF_F_ONECOMP_FILL)) return fail(MCALF_E_INVALID, "ONECOMP and ONECOMP_FILL are exclusive");
+    if ((flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) && (flags & MCALF_F_UNIT_CUBE))
+        return fail(MCALF_E_INVALID, "ONECOMP rows are physical parameters, not unit-cube draws");
+    CU(cudaSetDevice(c->device));
+    const size_t esize = (flags & MCALF_F_FLUX_F64) ? 8 : 4;
+
+    if (flags & MCALF_F_ON_DEVICE) {
+        Slot &s = c->slot[0];
+        int rc = ensure_slot(c, s, B, ld, 0, false);
+        if (rc) return rc;
+        c->last_slot = 0;
+        return enqueue(c, s, (cudaStream_t)stream, params, B, ld, flags, logl, chi2, flux);
+    }
+
+    // host pointers: slices pipelined through two pinned staging slots, one stream each, so the
+    // H2D of slice k+1 and the D2H of slice k-1 overlap the kernel of slice k
+    long long slice = c->slice;
+    if (flux) slice = std::max<long long>(1, std::min<long long>(slice, (long long)((64u << 20) / ((size_t)c->P.npix * esize))));
+    slice = std::min(slice, B);
+    const size_t flux_bytes = flux ? (size_t)slice * c->P.npix * esize : 0;
+    struct Pending { long long off = 0, n = 0; bool live = false; } pend[NBUF];
+    auto drain = [&](int k) -> int {
+        Slot &s = c->slot[k];
+        if (!pend[k].live) return MCALF_OK;
+        CU(cudaEventSynchronize(s.done));
+        if (logl) memcpy(logl + pend[k].off, s.h_out, sizeof(double) * (size_t)pend[k].n);
+        if (chi2) memcpy(chi2 + pend[k].off, s.h_out + pend[k].n, sizeof(double) * (size_t)pend[k].n);
+        if (flux) memcpy((char *)flux + (size_t)pend[k].off * c->P.npix * esize, s.h_flux, (size_t)pend[k].n * c->P.npix * esize);
+        pend[k].live = false;
+        return MCALF_OK;
+    };
+    int k = 0;
+    for (long long off = 0; off < B; off += slice, k ^= 1) {
+        const long long n = std::min(slice, B - off);
+        Slot &s = c->slot[k];
+        int rc = drain(k);
+        if (rc) return rc;
+        rc = ensure_slot(c, s, slice, ld, flux_bytes, true);
+        if (rc) return rc;
+        memcpy(s.h_params, params + off * ld, sizeof(double) * (size_t)n * (size_t)ld);
+        CU(cudaMemcpyAsync(s.d_params, s.h_params, sizeof(double) * (size_t)n * (size_t)ld, cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue(c, s, s.stream, s.d_params, n, ld, flags, s.d_out, s.d_out + n, flux ? s.d_flux : nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        if (flux) CU(cudaMemcpyAsync(s.h_flux, s.d_flux, (size_t)n * c->P.npix * esize, cudaMemcpyDeviceToHost, s.stream));
+        CU(cudaEventRecord(s.done, s.stream));
+        pend[k].off = off;
+        pend[k].n = n;
+        pend[k].live = true;
+        c->last_slot = k;
+    }
+    for (int j = 0; j < NBUF; ++j) {
+        int rc = drain(j);
+        if (rc) return rc;
+    }
+    return MCALF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mcalf_abi_version(void) { return MCALF_ABI_VERSION; }
+const char *mcalf_last_error(void) { return g_err; }
+
+int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
+    if (!p || !out) return fail(MCALF_E_INVALID, "null argument");
+    *out = nullptr;
+    if (p->abi_version != MCALF_ABI_VERSION) return fail(MCALF_E_INVALID, "ABI version %d, library is %d", p->abi_version, MCALF_ABI_VERSION);
+    if (p->npix < 1 || !p->wave || !p->flux || !p->err) return fail(MCALF_E_INVALID, "empty spectrum");
+    if (p->nlines < 1 || !p->line_wrest || !p->line_f || !p->line_gamma) return fail(MCALF_E_INVALID, "no lines");
+    if (p->ncompmax < 0 || p->nfill < 0) return fail(MCALF_E_INVALID, "negative component count");
+    const int startind = (p->free_specres ? 1 : 0) + (p->free_cont ? 1 : 0);          // hires_fitter.py:169-174
+    const int ndim = startind + 1 + 3 * (p->ncompmax + p->nfill);                     // :200
+    if (p->ndim != ndim) return fail(MCALF_E_INVALID, "ndim %d inconsistent with the layout (%d)", p->ndim, ndim);
+    if (!p->bounds_lo || !p->bounds_hi) return fail(MCALF_E_INVALID, "null bounds");
+    if (!(p->velstep > 0.0)) return fail(MCALF_E_INVALID, "velstep must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1)
+        return fail(MCALF_E_NODEVICE, "no CUDA device (%s): this library never computes on the host", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(MCALF_E_INVALID, "device %d out of range (%d devices)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    mcalf_ctx *c = new mcalf_ctx();
+    c->device = device;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    DevProblem &P = c->P;
+    const int npix = p->npix;
+    P.npix = npix;
+    P.npix4 = (npix + 3) & ~3;
+    P.nlines = p->nlines;
+    P.ncompmax = p->ncompmax;
+    P.nfill = p->nfill;
+    P.ndim = ndim;
+    P.ndim_pad = (std::max(ndim, 5) + 1) & ~1;
+    P.startind = startind;
+    P.endind = startind + 3 * p->ncompmax + 1;                                         // :176
+    P.free_specres = p->free_specres ? 1 : 0;
+    P.free_cont = p->free_cont ? 1 : 0;
+    P.asymmlike = p->asymmlike ? 1 : 0;
+    P.fixed_specres = p->fixed_specres;
+    P.fixed_cont = p->fixed_cont;
+    P.velstep = p->velstep;
+    P.asym_t5 = p->asym_thresh5;
+    P.asym_t4 = p->asym_thresh4;
+    P.a_max = A_MAX_LIMIT;
+    P.eps_cull = 0.0f;
+    P.Lmax = std::max(p->ncompmax * p->nlines + p->nfill, std::max(p->nlines, 1));
+    P.lam_ref = p->wave[npix / 2];
+    if (!(P.lam_ref > 0.0)) return fail(MCALF_E_INVALID, "non-positive wavelength");
+
+    // largest LSF half-width any sample may need (hires_fitter.py:454-459)
+    double max_res = p->max_specres;
+    if (!(max_res > 0.0)) {
+        max_res = p->fixed_specres;
+        if (p->free_specres) max_res = std::max(p->bounds_lo[0], p->bounds_hi[0]);
+    }
+    int nmax = (int)ceil(TRUNC_SIGMAS_H * (max_res / FWHM_TO_SIGMA_H) / p->velstep) + 1;
+    if (nmax < 1) nmax = 1;
+    P.nmax = nmax;
+    P.nmax4 = (nmax + 3) & ~3;
+    P.halo = P.nmax4;
+
+    // per-pixel tables
+    std::vector<double> wave(p->wave, p->wave + npix), obj(npix), w(npix), obj_raw(p->flux, p->flux + npix), isig(npix);
+    std::vector<float4> pix(npix);
+    double csum = 0.0;
+    P.chi2_add = 0.0;
+    for (int i = 0; i < npix; ++i) {
+        if (!(wave[i] > 0.0)) return fail(MCALF_E_INVALID, "non-positive wavelength at pixel %d", i);
+        const double f = p->flux[i], er = p->err[i];
+        isig[i] = 1.0 / er;
+        // nansum (:294) drops the pixel when its term is NaN: NaN flux, NaN error, or zero error
+        // (w = inf gives inf - inf)
+        const bool valid = !(f != f) && !(er != er) && er != 0.0;
+        if (valid) {
+            const double wi = 1.0 / (er * er);
+            obj[i] = f;
+            w[i] = wi;
+            csum += -log(wi) + log(2.0 * 3.14159265358979323846);
+        } else {
+            obj[i] = 0.0;
+            w[i] = 0.0;
+            // chi2 (:246) has no -log(w) term: a zero-error pixel contributes inf*(resid^2) = +inf there
+            if (er == 0.0 && !(f != f)) P.chi2_add = INFINITY;
+        }
+        const float oh = (float)obj[i];
+        pix[i] = make_float4(oh, (float)(obj[i] - (double)oh), (float)w[i], 0.0f);
+    }
+    P.logC = -0.5 * csum;
+
+    // chunks: <= 256 consecutive pixels whose rho = lam_ref/lambda spans at most 2^-9
+    std::vector<ChunkDesc> chunks;
+    std::vector<float> dhi(npix), dlo(npix);
+    {
+        int start = 0;
+        while (start < npix) {
+            double rmin = P.lam_ref / wave[start], rmax = rmin;
+            int len = 1;
+            while (start + len < npix && len < 256) {
+                const double r = P.lam_ref / wave[start + len];
+                const double nmin = std::min(rmin, r), nmx = std::max(rmax, r);
+                if (nmx - nmin > 1.0 / 512.0) break;
+                rmin = nmin;
+                rmax = nmx;
+                ++len;
+            }
+            ChunkDesc cd;
+            cd.start = start;
+            cd.len = len;
+            cd.rho_s = 0.5 * (rmin + rmax);
+            float dmin = 3e38f, dmax = -3e38f;
+            for (int i = start; i < start + len; ++i) {
+                const double d = P.lam_ref / wave[i] - cd.rho_s;
+                dhi[i] = (float)d;
+                dlo[i] = (float)(d - (double)dhi[i]);
+                dmin = std::min(dmin, dhi[i]);
+                dmax = std::max(dmax, dhi[i]);
+            }
+            // widen by one ulp-ish so the classification bound covers the dropped low part
+            cd.dmin = dmin - fabsf(dmin) * 1e-6f - 1e-12f;
+            cd.dmax = dmax + fabsf(dmax) * 1e-6f + 1e-12f;
+            chunks.push_back(cd);
+            start += len;
+        }
+    }
+    P.nchunks = (int)chunks.size();
+
+    std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),
+        lg(p->line_gamma, p->line_gamma + p->nlines);
+    lw.push_back(p->fill_wrest);
+    lf.push_back(p->fill_f);
+    lg.push_back(p->fill_gamma);
+    std::vector<double> blo(p->bounds_lo, p->bounds_lo + ndim), bhi(p->bounds_hi, p->bounds_hi + ndim);
+
+    int rc;
+#define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) { mcalf_destroy(c); return rc; }
+    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(pix, pix) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
+    UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)
+#undef UP
+    e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
+    if (e != cudaSuccess) { mcalf_destroy(c); return fail(MCALF_E_CUDA, "stats buffer: %s", cudaGetErrorString(e)); }
+    if ((rc = choose_launch(c)) != MCALF_OK) { mcalf_destroy(c); return rc; }
+    *out = c;
+    return MCALF_OK;
+}
+
+void mcalf_destroy(mcalf_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (Slot &s : c->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.h_params) cudaFreeHost(s.h_params);
+        if (s.d_params) cudaFree(s.d_params);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_flux) cudaFreeHost(s.h_flux);
+        if (s.d_flux) cudaFree(s.d_flux);
+        if (s.counters) cudaFree(s.counters);
+        if (s.fallback) cudaFree(s.fallback);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.k0) cudaEventDestroy(s.k0);
+        if (s.k1) cudaEventDestroy(s.k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (void *d : c->allocs) cudaFree(d);
+    if (c->d_stats) cudaFree(c->d_stats);
+    delete c;
+}
+
+int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags, void *stream,
+                        double *logl_out, double *chi2_out) {
+    if (!logl_out && !chi2_out && B > 0) return fail(MCALF_E_INVALID, "no output buffer");
+    const uint32_t allowed = MCALF_F_UNIT_CUBE | MCALF_F_ON_DEVICE | MCALF_F_FP64 | MCALF_F_TARGONLY | MCALF_F_NO_TRUNC;
+    if (flags & ~allowed) return fail(MCALF_E_INVALID, "flag 0x%x not valid for mcalf_loglike_batch", flags & ~allowed);
+    return run_batch(ctx, params, B, ld, flags, stream, logl_out, chi2_out, nullptr);
+}
+
+int mcalf_model_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags, void *stream, void *flux_out) {
+    if (!flux_out && B > 0) return fail(MCALF_E_INVALID, "null flux_out");
+    return run_batch(ctx, params, B, ld, flags, stream, nullptr, nullptr, flux_out);
+}
+
+int mcalf_prior_transform_batch(mcalf_ctx *c, const double *cube, int64_t B, int64_t ld, uint32_t flags, void *stream, double *theta_out) {
+    if (!c) return fail(MCALF_E_INVALID, "null context");
+    if (B < 0) return fail(MCALF_E_INVALID, "negative batch size");
+    if (B == 0) return MCALF_OK;
+    if (!cube || !theta_out) return fail(MCALF_E_INVALID, "null buffer");
+    if (ld < c->P.ndim) return fail(MCALF_E_INVALID, "ld (%lld) smaller than ndim (%d)", (long long)ld, c->P.ndim);
+    CU(cudaSetDevice(c->device));
+    if (flags & MCALF_F_ON_DEVICE) {
+        CU(launch_prior(c->P, cube, B, ld, flags, theta_out, (cudaStream_t)stream));
+        c->kernel_launches += 1;
+        return MCALF_OK;
+    }
+    double *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc((void **)&d_in, sizeof(double) * (size_t)B * (size_t)ld));
+    cudaError_t e = cudaMalloc((void **)&d_out, sizeof(double) * (size_t)B * (size_t)c->P.ndim);
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, cube, sizeof(double) * (size_t)B * (size_t)ld, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_prior(c->P, d_in, B, ld, flags, d_out, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(theta_out, d_out, sizeof(double) * (size_t)B * (size_t)c->P.ndim, cudaMemcpyDeviceToHost);
+    cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    if (e != cudaSuccess) return fail(MCALF_E_CUDA, "prior transform: %s", cudaGetErrorString(e));
+    c->kernel_launches += 1;
+    return MCALF_OK;
+}
+
+int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_t n, double *h_out) {
+    if (n < 0 || (n > 0 && (!u || !a || !h_out))) return fail(MCALF_E_INVALID, "bad argument");
+    if (n == 0) return MCALF_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(MCALF_E_NODEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    double *d = nullptr;
+    CU(cudaMalloc((void **)&d, sizeof(double) * 3 * (size_t)n));
+    cudaError_t e = cudaMemcpy(d, u, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d + n, a, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_voigt_h(mode, d, d + n, n, d + 2 * n, nullptr);
+    if (e == cudaSuccess) e = cudaMemcpy(h_out, d + 2 * n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(MCALF_E_CUDA, "voigt_h: %s", cudaGetErrorString(e));
+    return MCALF_OK;
+}
+
+int mcalf_ffma_peak(int device, double *tflops_out) {
+    if (!tflops_out) return fail(MCALF_E_INVALID, "null output");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(MCALF_E_NODEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int threads = 1024, grid = prop.multiProcessorCount * 2, iters = 4096;
+    float *d = nullptr;
+    CU(cudaMalloc((void **)&d, sizeof(float) * (size_t)grid * threads));
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        CU(cudaEventRecord(a));
+        CU(launch_ffma_peak(d, grid, threads, iters, nullptr));
+        CU(cudaEventRecord(b));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        const double flop = 2.0 * 128.0 * (double)iters * (double)grid * threads;
+        if (rep > 0) best = std::max(best, flop / (ms * 1e-3) * 1e-12);
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    *tflops_out = best;
+    return MCALF_OK;
+}
+
+int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
+    if (!c || !out) return fail(MCALF_E_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    memset(out, 0, sizeof(*out));
+    unsigned long long h[8];
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost));
+    out->kernel_launches = c->kernel_launches;
+    out->samples = c->samples;
+    out->samples_fp64 = c->samples_fp64;
+    out->evals_total = h[0];
+    out->evals_wing = h[1];
+    out->evals_mixed = h[2];
+    out->evals_core = h[3];
+    out->evals_culled = h[4];
+    if (c->last_slot >= 0) {
+        float ms = 0.f;
+        Slot &s = c->slot[c->last_slot];
+        if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->last_kernel_ms = ms;
+    }
+    return MCALF_OK;
+}
+
+int mcalf_reset_stats(mcalf_ctx *c) {
+    if (!c) return fail(MCALF_E_INVALID, "null context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
+    c->kernel_launches = c->samples = c->samples_fp64 = 0;
+    return MCALF_OK;
+}
+
+int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
+    if (!c || !name) return fail(MCALF_E_INVALID, "null argument");
+    CU(cudaSetDevice(c->device));
+    if (!strcmp(name, "cull_eps")) {
+        if (!(value >= 0.0)) return fail(MCALF_E_INVALID, "cull_eps must be >= 0");
+        c->P.eps_cull = (float)value;
+    } else if (!strcmp(name, "a_max")) {
+        if (!(value >= 0.0) || value > A_MAX_LIMIT) return fail(MCALF_E_INVALID, "a_max must be in [0, %g]", A_MAX_LIMIT);
+        c->P.a_max = value;
+    } else if (!strcmp(name, "collect_stats")) {
+        c->collect_stats = value != 0.0;
+    } else if (!strcmp(name, "threads")) {
+        const int t = (int)value;
+        if (t < 0 || t > 1024 || (t % 32)) return fail(MCALF_E_INVALID, "threads must be a multiple of 32 in [0, 1024]");
+        const int old = c->threads_opt;
+        c->threads_opt = t;
+        int rc = choose_launch(c);
+        if (rc) { c->threads_opt = old; choose_launch(c); return rc; }
+    } else if (!strcmp(name, "ctas_per_sm")) {
+        if (value < 0) return fail(MCALF_E_INVALID, "ctas_per_sm must be >= 0");
+        c->ctas_opt = (int)value;
+        return choose_launch(c);
+    } else if (!strcmp(name, "slice")) {
+        if (value < 1) return fail(MCALF_E_INVALID, "slice must be >= 1");
+        c->slice = (long long)value;
+    } else {
+        return fail(MCALF_E_INVALID, "unknown option '%s'", name);
+    }
+    return MCALF_OK;
+}
+
+int mcalf_get_option(mcalf_ctx *c, const char *name, double *value) {
+    if (!c || !name || !value) return fail(MCALF_E_INVALID, "null argument");
+    if (!strcmp(name, "cull_eps")) *value = c->P.eps_cull;
+    else if (!strcmp(name, "a_max")) *value = c->P.a_max;
+    else if (!strcmp(name, "collect_stats")) *value = c->collect_stats;
+    else if (!strcmp(name, "threads")) *value = c->threads;
+    else if (!strcmp(name, "ctas_per_sm")) *value = c->ctas_per_sm;
+    else if (!strcmp(name, "slice")) *value = (double)c->slice;
+    else return fail(MCALF_E_INVALID, "unknown option '%s'", name);
+    return MCALF_OK;
+}
+
+int mcalf_get_geometry(mcalf_ctx *c, int64_t *out) {
+    if (!c || !out) return fail(MCALF_E_INVALID, "null argument");
+    out[0] = c->P.npix;
+    out[1] = c->P.nchunks;
+    out[2] = c->threads;
+    out[3] = c->ctas_per_sm;
+    out[4] = c->sm_count;
+    out[5] = (int64_t)c->smem_fast;
+    out[6] = c->P.halo;
+    out[7] = c->P.Lmax;
+    return MCALF_OK;
+}
+
+int mcalf_host_alloc(void **ptr, uint64_t bytes) {
+    if (!ptr) return fail(MCALF_E_INVALID, "null argument");
+    CU(cudaMallocHost(ptr, bytes ? bytes : 1));
+    return MCALF_OK;
+}
+
+int mcalf_host_free(void *ptr) {
+    if (ptr) CU(cudaFreeHost(ptr));
+    return MCALF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// mcalf_device.h -- structures shared by the kernels (mcalf_kernels.cu) and the C-ABI host layer
+// (mcalf_api.cu).  Internal: the public interface is include/mcalf_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mcalf_b200.h"
+
+namespace mcalf {
+
+// <= 256 consecutive pixels of the concatenated fit-window array sharing one fp64 reference rho_s
+struct ChunkDesc {
+    int start, len;
+    float dmin, dmax;     // range of delta = rho - rho_s over the chunk
+    double rho_s;
+};
+
+// Everything als_fitter.__init__ leaves behind (hires_fitter.py:65-200), in device form.
+struct DevProblem {
+    int npix, npix4, nchunks, nlines;
+    int ncompmax, nfill, ndim, ndim_pad;
+    int startind, endind, free_specres, free_cont;
+    int asymmlike, halo, nmax, nmax4;
+    int Lmax, pad_;
+    float eps_cull, padf_;
+    double fixed_specres, fixed_cont, velstep, lam_ref;
+    double logC, asym_t5, asym_t4, a_max;
+    double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
+    const float *delta_hi, *delta_lo;   // [npix] rho_i - rho_s(chunk) as a two-float
+    const float4 *pix;                  // [npix] {obj_hi, obj_lo, w, 0}; obj = w = 0 on dropped pixels
+    const ChunkDesc *chunks;            // [nchunks]
+    const double *wave, *obj, *w;       // [npix] fp64 copies for the check kernel (obj = w = 0 on dropped pixels)
+    const double *obj_raw, *isig;       // [npix] untouched flux and 1/err for the Asymmlike counts
+    const double *line_wrest, *line_f, *line_gamma;   // [nlines + 1], the last entry is the filler line
+    const double *blo, *bhi;            // [ndim] prior bounds
+};
+
+struct BatchArgs {
+    const double *params;
+    long long B, ld;
+    uint32_t flags, pad_;
+    double *logl_out, *chi2_out;
+    void *flux_out;
+    unsigned int *work_counter;         // zeroed before the launch
+    unsigned int *fallback_count;       // zeroed before the launch
+    int *fallback_list;                 // [B]
+    unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled} evaluations
+};
+
+size_t fast_smem_bytes(const DevProblem &P, int nwarps);
+size_t fp64_smem_bytes(const DevProblem &P);
+cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes);
+cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t launch_fp64(const DevProblem &P, const BatchArgs &Bt, const int *idx_list, const unsigned int *idx_count, int grid,
+                        size_t smem, cudaStream_t st);
+cudaError_t launch_prior(const DevProblem &P, const double *cube, long long B, long long ld, uint32_t flags, double *out,
+                         cudaStream_t st);
+cudaError_t launch_voigt_h(int mode, const double *u, const double *a, long long n, double *out, cudaStream_t st);
+cudaError_t launch_ffma_peak(float *out, int grid, int threads, int iters, cudaStream_t st);
+
+}  // namespace mcalf

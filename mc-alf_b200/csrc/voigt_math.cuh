@@ -94,6 +94,26 @@ MCALF_HD float exp_neg32(float x, float xlo) {
     return p * sc.f;
 }
 
+// 1 - exp(-x) for x >= 0 (the absorption depth of optical depth x), relative accuracy ~1e-7 even for
+// x -> 0: with exp(-x) = 2^-n (1 + r q(r)) the depth is (1 - 2^-n) - 2^-n r q(r), and 1 - 2^-n is exact.
+MCALF_HD float depth32(float x) {
+    const float c[8] = MCALF_EXPM_C;
+    x = fminf(x, 88.0f);
+    float n = rintf(x * 1.44269504088896341f);
+    float r = fma32(n, -0.693145751953125f, x);
+    r = fma32(n, -1.42860676533018702e-06f, r);
+    float q = fma32(c[7], r, c[6]);
+    q = fma32(q, r, c[5]);
+    q = fma32(q, r, c[4]);
+    q = fma32(q, r, c[3]);
+    q = fma32(q, r, c[2]);
+    q = fma32(q, r, c[1]);
+    int e = 127 - (int)n;               // n in [0,127]
+    union { int32_t i; float f; } sc;
+    sc.i = e << 23;
+    return fma32(-sc.f, r * q, 1.0f - sc.f);
+}
+
 MCALF_HD G1Row g1_row(int j) {
 #if defined(__CUDA_ARCH__)
     const float4 v = __ldg(reinterpret_cast<const float4 *>(g1_tab_dev) + j);
@@ -189,15 +209,21 @@ MCALF_HD double voigt_h64(double a, double u) {
 //   u = A (rho - rho_c),  rho = lam_ref/lambda,  rho_c = lam_ref/(wrest (1+z)),  A = (c/b) wrest (1+z)/lam_ref
 //   tau = kappa H(a,u),  kappa = 0.014971475 10^logN f wrest_cm / b_cms,  a = gamma wrest_cm / (4 pi b_cms)
 // (algebraically identical to hires_fitter.py:355-365).
+//
+// Pixel coordinates are stored per CHUNK (<= 256 consecutive pixels of one fit window): the context
+// keeps rho_s (fp64, the chunk's reference) and delta_i = rho_i - rho_s as a two-float (hi, lo).
+// Per (line, chunk) the kernel forms U = A (rho_s - rho_c) in fp64 once, so that per pixel
+//   u = fma(A_hi, delta_hi, U_hi)                                   (one FMA; wing accuracy)
+//   u = (A_hi, A_lo) * (delta_hi, delta_lo) + (U_hi, U_lo)          (two-float; line core)
 // ---------------------------------------------------------------------------------------------
 struct Line64 {
     double A, rc, kappa, a;
 };
 
-struct Line32 {
-    float A_hi, A_lo, rc_hi, rc_lo;   // two-float A and rho_c
-    float U0, c1, a, a2;              // U0 = -A*rho_c; c1 = kappa*a/sqrt(pi)
-    float kappa, d_near, d_cull, c1w; // c1w = c1 * wing_qp(S_CUT) (what the clamped wing added)
+// 32 bytes: what the mixed (core-containing) path reads per line
+struct LineP {
+    float A_hi, a2, c1, kappa;   // c1 = kappa*a/sqrt(pi): the wing amplitude
+    float A_lo, a, pad0, pad1;
 };
 
 MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, double f, double gamma,
@@ -207,7 +233,12 @@ MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, 
     const double wrest_cm = wrest * 1e-8, b_cms = b_kms * 1e5;
     L.A = (C_KMS / b_kms) * (lamc / lam_ref);
     L.rc = lam_ref / lamc;
-    L.kappa = TAU_CONST * pow(10.0, logN) * f * wrest_cm / b_cms;
+#if defined(__CUDA_ARCH__)
+    const double cold = exp10(logN);
+#else
+    const double cold = pow(10.0, logN);
+#endif
+    L.kappa = TAU_CONST * cold * f * wrest_cm / b_cms;
     L.a = gamma * wrest_cm / (4.0 * PI_D * b_cms);
     return L;
 }
@@ -217,36 +248,67 @@ MCALF_HD void split2(double v, float &hi, float &lo) {
     lo = (float)(v - (double)hi);
 }
 
-// eps_far: optical-depth error allowed to the one-FMA far form; eps_cull: optical depth below
-// which a line is skipped on a segment (0 = never).
-MCALF_HD Line32 line_setup32(const Line64 &L, double eps_far, double eps_cull) {
-    Line32 o;
+MCALF_HD LineP line_pack(const Line64 &L) {
+    LineP o;
     split2(L.A, o.A_hi, o.A_lo);
-    split2(L.rc, o.rc_hi, o.rc_lo);
-    o.U0 = (float)(-L.A * L.rc);
-    const double c1 = L.kappa * L.a / SQRTPI_D;
-    o.c1 = (float)c1;
     o.a = (float)L.a;
     o.a2 = (float)(L.a * L.a);
+    o.c1 = (float)(L.kappa * L.a / SQRTPI_D);
     o.kappa = (float)L.kappa;
-    const float wcut = 0.0288810f;  // ~ q P(q) at s = S_CUT, recomputed exactly below
-    (void)wcut;
-    o.c1w = o.c1 * wing_qp(S_CUT);
-    // far form  u = fma(A_hi, rho_hi, U0): |du| <= 3 * 2^-24 * |A rho|  (rho_hi, product, U0 roundings)
-    // => |dtau| <= 2 c1 |du| / u^3 * 1.05.  Need u >= u_far for |dtau| <= eps_far; never inside the core.
-    const double du = 3.0 * 5.97e-8 * fabs(L.A) * 1.001 * (L.rc > 1.0 ? L.rc : 1.0);
-    double u_far = cbrt(2.1 * c1 * du / eps_far);
-    const double u_core = sqrt((double)S_CUT) * 1.02 + 2.0 * du;
-    if (!(u_far > u_core)) u_far = u_core;
-    o.d_near = (float)(u_far / fabs(L.A) * 1.0001);
-    if (eps_cull > 0.0) {
-        double u_cull = sqrt(1.05 * c1 / eps_cull);
-        if (!(u_cull > u_far)) u_cull = u_far;
-        o.d_cull = (float)(u_cull / fabs(L.A) * 1.0001);
-    } else {
-        o.d_cull = 3.0e38f;
-    }
+    o.pad0 = o.pad1 = 0.0f;
     return o;
+}
+
+// |u| below which a chunk is treated as containing line-core pixels (S_CUT = 36 plus a margin that
+// covers the one-FMA coordinate's error).
+constexpr float U_CORE_MARGIN = 6.01f;
+
+// Class of a (line, chunk) pair from the u range the chunk spans: 0 = culled, 1 = wing only,
+// 2 = mixed (some pixel may have u^2 + a^2 < S_CUT).
+MCALF_HD int chunk_class(float A_hi, float U_hi, float dmin, float dmax, float c1, float eps_cull) {
+    const float u1 = fma32(A_hi, dmin, U_hi), u2 = fma32(A_hi, dmax, U_hi);
+    const float lo = fminf(u1, u2), hi = fmaxf(u1, u2);
+    if (!(lo > U_CORE_MARGIN || hi < -U_CORE_MARGIN)) return 2;   // also catches NaN
+    const float m = fminf(fabsf(lo), fabsf(hi));
+    // tau <= c1 q P(q) <= 1.05 c1 / u^2 on the chunk
+    if (1.05f * c1 < eps_cull * m * m) return 0;
+    return 1;
+}
+
+// one wing evaluation: tau contribution of a line at s = u^2 + a^2 >= S_CUT
+MCALF_HD float wing_tau(float c1, float s) {
+    const float w[5] = MCALF_WING_P;
+    float q = rcp32(s);
+    float p = fma32(w[4], q, w[3]);
+    p = fma32(p, q, w[2]);
+    p = fma32(p, q, w[1]);
+    p = fma32(p, q, w[0]);
+    return (c1 * q) * p;
+}
+
+// two-float u = A*delta + U for the line core
+MCALF_HD void core_u2(float A_hi, float A_lo, float d_hi, float d_lo, float U_hi, float U_lo, float &uh,
+                      float &ul) {
+    const float ph = A_hi * d_hi;
+    float pl = fma32(A_hi, d_hi, -ph);
+    pl = fma32(A_hi, d_lo, pl);
+    pl = fma32(A_lo, d_hi, pl);
+    const float sh = U_hi + ph;
+    const float bb = sh - U_hi;
+    const float se = (U_hi - (sh - bb)) + (ph - bb);
+    uh = sh;
+    ul = se + (pl + U_lo);
+}
+
+// tau contribution of one line at one pixel of a mixed chunk
+MCALF_HD float mixed_tau(const LineP &L, float U_hi, float U_lo, float d_hi, float d_lo, bool &core) {
+    const float u = fma32(L.A_hi, d_hi, U_hi);
+    const float s = fma32(u, u, L.a2);
+    core = s < S_CUT;
+    if (!core) return wing_tau(L.c1, s);
+    float uh, ul;
+    core_u2(L.A_hi, L.A_lo, d_hi, d_lo, U_hi, U_lo, uh, ul);
+    return L.kappa * core_h32(L.a, L.a2, uh, ul);
 }
 
 // LSF geometry (hires_fitter.py:452-459): sigma in pixels and half-width n = ceil(3.0348 sigma).

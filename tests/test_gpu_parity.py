@@ -1,0 +1,208 @@
+"""GPU: the CUDA path (through the C-ABI, via the als_fitter mirror) against the oracle and against
+golden outputs of the unmodified reference.  Tolerances are BASELINE.json's: model flux within 1e-6
+of the continuum, |dlogL| <= 1e-6 |logL| (with an absolute floor of 1e-6 |C|, C the constant term,
+where logL crosses zero -- SURVEY.md section 7 hard part 3)."""
+import numpy as np
+import pytest
+
+from oracle import mcalf_oracle as orc
+from tests.cases import ALL_TAGS, case
+
+pytestmark = pytest.mark.gpu
+
+FLUX_TOL = 1e-6
+LOGL_RTOL = 1e-6
+
+
+def fitters(tag, **extra_gpu):
+    import mcalf_b200
+    spec, kw, extra = case(tag)
+    o = orc.OracleFitter(spec, **kw, **extra)
+    g = mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                              **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                 if k not in ("fitrange", "fitlines", "ncomp")}, **extra, **extra_gpu)
+    return o, g
+
+
+def logl_close(got, ref, const):
+    got, ref = np.asarray(got), np.asarray(ref)
+    assert np.array_equal(np.isinf(got), np.isinf(ref)), (got, ref)
+    fin = np.isfinite(ref)
+    tol = LOGL_RTOL * np.maximum(np.abs(ref[fin]), abs(const))
+    err = np.abs(got[fin] - ref[fin])
+    assert (err <= tol).all(), "max |dlogL|/tol = %g" % (err / tol).max()
+    return (err / np.maximum(np.abs(ref[fin]), 1e-300)).max() if fin.any() else 0.0
+
+
+def const_term(o):
+    with np.errstate(all="ignore"):
+        w = 1.0 / o.obj_noise ** 2
+        return -0.5 * np.nansum(np.where(np.isnan(o.obj), np.nan, -np.log(w) + np.log(2 * np.pi)))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("tag", ALL_TAGS)
+def test_golden_reference_outputs(tag, precision, golden):
+    """logL, chi2 and model flux computed by the UNMODIFIED reference (tests/golden)."""
+    o, g = fitters(tag, precision=precision)
+    P = golden[tag + "_P"]
+    assert g.velstep == pytest.approx(float(golden[tag + "_velstep"]), rel=1e-14)
+    assert np.array_equal(np.column_stack([g._blo, g._bhi]), golden[tag + "_bounds"])
+    logl, chi2 = g.lnlhood_batch(P, return_chi2=True)
+    logl_close(logl, golden[tag + "_logL"], const_term(o))
+    ref_chi2 = golden[tag + "_chi2"]
+    assert np.allclose(chi2, ref_chi2, rtol=2e-6 if precision == "fp32" else 1e-10)
+    flux = golden[tag + "_flux"]
+    got = g.reconstruct_spec_batch(P[:flux.shape[0]])
+    cont = np.array([o.unpack(p)[1] for p in P[:flux.shape[0]]])[:, None]
+    err = np.abs(got - flux) / np.abs(cont)
+    assert err.max() <= (FLUX_TOL if precision == "fp32" else 1e-11), err.max()
+    # the scalar callbacks are batches of one
+    assert g.lnlhood_worker(P[0]) == logl[0] or (np.isinf(logl[0]) and np.isinf(g.lnlhood_worker(P[0])))
+    assert g.lnlhood_pc(P[0])[1] == []
+    assert np.array_equal(g.reconstruct_spec(P[0]), got[0])
+
+
+def test_known_answers_testdata():
+    """the reference's two mock spectra at their truth parameters."""
+    o, g = fitters("cfg1_truth")
+    assert g.lnlhood_worker(np.array([1.0, 13.8, 3.0, 15.0])) == pytest.approx(5001.865105876514, rel=1e-6)
+    assert g.chi2(np.array([1.0, 13.8, 3.0, 15.0])) == pytest.approx(1956.6353392519727, rel=2e-6)
+    o, g = fitters("cfg2_truth")
+    p = np.array([10, 13.6, 2.999, 17.5, 13.0, 2.9995, 8, 13.8, 3.0, 20, 13.6, 3.001, 25, 13.2, 3.0005, 15, 13.4, 3.0015, 30,
+                  13.5, 3.002, 10, 14.0, 3.0025, 25, 14.2, 3.0035, 15, 13.7, 3.0039, 20], dtype=float)
+    assert g.lnlhood_worker(p) == pytest.approx(4991.860095571161, rel=1e-6)
+    assert g.chi2(p) == pytest.approx(1976.6453598626786, rel=2e-6)
+
+
+def test_mock_spectrum_is_model_plus_noise():
+    """The reference's own golden vector through the CUDA model: Flux - N(0,.02;seed 42) == model(truth)."""
+    o, g = fitters("cfg1_truth")
+    np.random.seed(42)
+    noise = np.random.normal(0, 0.02, size=len(g.obj_wl))
+    m = g.reconstruct_spec(np.array([1.0, 13.8, 3.0, 15.0]))
+    assert np.abs(g.obj - noise - m).max() < FLUX_TOL
+    m64 = g.reconstruct_spec_batch(np.array([[1.0, 13.8, 3.0, 15.0]]), fp64=True)[0]
+    assert np.abs(g.obj - noise - m64).max() < 1e-11   # the reference's own u formula is noisy at 1e-12
+
+
+@pytest.mark.parametrize("cfg,B", [(1, 512), (2, 256), (3, 24), (4, 32)])
+def test_prior_draws_vs_oracle(cfg, B):
+    """Fresh prior draws (unit cube on the GPU, _scale_cube_pc in the oracle) at every BASELINE config."""
+    o, g = fitters("cfg%d" % cfg)
+    U = np.random.default_rng(100 + cfg).random((B, o.ndim))
+    P = np.array([o._scale_cube_pc(u) for u in U])
+    assert np.array_equal(g.prior_transform_batch(U), P)            # bit-exact prior transform
+    assert np.array_equal(np.array([g._scale_cube_pc(u) for u in U]), P)
+    ref = np.array([o.lnlhood_worker(p) for p in P])
+    got = g.lnlhood_batch(U, unit_cube=True)
+    assert np.array_equal(got, g.lnlhood_batch(P))                  # same kernel either way
+    worst = logl_close(got, ref, const_term(o))
+    got64 = g.lnlhood_batch(P, fp64=True)
+    assert np.allclose(got64, ref, rtol=1e-10)
+    nf = min(B, 8)
+    flux = g.reconstruct_spec_batch(P[:nf])
+    for i in range(nf):
+        m = o.reconstruct_spec(P[i])
+        assert np.abs(flux[i] - m).max() / abs(o.unpack(P[i])[1]) <= FLUX_TOL
+    print("cfg", cfg, "worst relative logL error", worst)
+
+
+def test_onecomp_and_targonly():
+    o, g = fitters("edge_gap")
+    m = g.reconstruct_onecomp(10.0, 0.97, 14.0, 2.99502, 12.0)
+    assert np.abs(m - o.reconstruct_onecomp(10.0, 0.97, 14.0, 2.99502, 12.0)).max() <= FLUX_TOL
+    m = g.reconstruct_onecomp_fill(10.0, 1.0, 15.0, 23.801, 1.5)
+    assert np.abs(m - o.reconstruct_onecomp(10.0, 1.0, 15.0, 23.801, 1.5, fill=True)).max() <= FLUX_TOL
+    # an LSF wider than the halo sized from the bounds (specres 45 vs 10): re-routed, still right
+    m = g.reconstruct_onecomp(45.0, 1.0, 14.0, 2.99502, 12.0)
+    assert np.abs(m - o.reconstruct_onecomp(45.0, 1.0, 14.0, 2.99502, 12.0)).max() <= 1e-9
+    p = np.array([2, 14.0, 2.99502, 12.0, 13.7, 2.99840, 20.0, 15.0, 23.7605, 9.0])
+    assert np.abs(g.reconstruct_spec(p, targonly=True) - o.reconstruct_spec(p, targonly=True)).max() <= FLUX_TOL
+    assert np.abs(g.reconstruct_spec(p) - o.reconstruct_spec(p)).max() <= FLUX_TOL
+
+
+def test_large_damping_routes_to_fp64():
+    """a > a_max is outside the fp32 series: the sample must land in the fp64 kernel, not be wrong."""
+    spec, kw, _ = case("cfg1")
+    atomic = {"FAKE 1548": (1548.204, 0.1899, 2.643e11)}    # gamma x1000 -> a ~ 0.13-3
+    import mcalf_b200
+    o = orc.OracleFitter(spec, **dict(kw, fitlines=["FAKE 1548"]), atomic=atomic)
+    g = mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], ["FAKE 1548"], list(kw["ncomp"]),
+                              specres=kw["specres"], contval=kw["contval"], atomic=atomic)
+    P = np.array([[1, 14.0, 3.0, 2.0], [1, 13.5, 3.001, 25.0], [1, 15.0, 2.9995, 1.0]])
+    g.reset_stats()
+    got = g.lnlhood_batch(P)
+    assert g.stats()["samples_fp64"] == 0 and g.stats()["kernel_launches"] == 2   # re-routed, not requested
+    ref = np.array([o.lnlhood_worker(p) for p in P])
+    assert np.allclose(got, ref, rtol=1e-9)
+    flux = g.reconstruct_spec_batch(P)
+    for i in range(3):
+        assert np.abs(flux[i] - o.reconstruct_spec(P[i])).max() < 1e-9
+
+
+def test_device_tensor_path_matches_host_path():
+    import torch
+    o, g = fitters("cfg2")
+    U = np.random.default_rng(5).random((300, o.ndim))
+    host = g.lnlhood_batch(U, unit_cube=True)
+    dev = g.lnlhood_batch(torch.from_numpy(U).cuda(), unit_cube=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), host)
+    g.set_option("slice", 64)           # several pipelined slices, ragged tail
+    assert np.array_equal(g.lnlhood_batch(U, unit_cube=True), host)
+    fh = g.reconstruct_spec_batch(U[:70], unit_cube=True, dtype=np.float32)
+    fd = g.reconstruct_spec_batch(torch.from_numpy(U[:70]).cuda(), unit_cube=True, dtype=torch.float32)
+    assert np.array_equal(fd.cpu().numpy(), fh)
+
+
+def test_launch_geometry_does_not_change_results():
+    """Per-sample results are independent of CTA size / CTAs per SM / batch composition (the
+    multi-GPU requirement: bit-identical whichever shard a sample lands in)."""
+    o, g = fitters("cfg3")
+    U = np.random.default_rng(9).random((64, o.ndim))
+    base = g.lnlhood_batch(U, unit_cube=True)
+    for threads in (128, 512, 1024):
+        g.set_option("threads", threads)
+        assert np.array_equal(g.lnlhood_batch(U, unit_cube=True), base)
+    g.set_option("threads", 0)
+    assert np.array_equal(g.lnlhood_batch(U[::-1].copy(), unit_cube=True)[::-1], base)
+    assert np.array_equal(g.lnlhood_batch(U[10:11], unit_cube=True), base[10:11])
+
+
+def test_empty_and_bad_input():
+    import mcalf_b200
+    o, g = fitters("cfg1")
+    assert g.lnlhood_batch(np.zeros((0, g.ndim))).shape == (0,)
+    with pytest.raises(ValueError):
+        g.lnlhood_batch(np.zeros((3, g.ndim - 1)))
+    out = g.lnlhood_batch(np.array([[1.0, np.nan, 3.0, 15.0]]))
+    assert np.isnan(out[0])
+    with pytest.raises(mcalf_b200.capi.McalfError):
+        g.set_option("no_such_option", 1)
+
+
+def test_full_size_properties():
+    """BASELINE cfg 4 at a bench-sized batch: properties that need no oracle run.
+    (i) a sample's logL does not depend on where it sits in the batch; (ii) ncomp = 0 gives the
+    continuum-only chi-square exactly; (iii) far-off-window components change nothing measurable;
+    (iv) chi2 and logL are tied by logL = C - chi2/2."""
+    o, g = fitters("cfg4")
+    B = 16384
+    U = np.random.default_rng(4).random((B, o.ndim))
+    logl, chi2 = g.lnlhood_batch(U, unit_cube=True, return_chi2=True)
+    assert np.isfinite(logl).all()
+    C = const_term(o)
+    assert np.allclose(logl, C - 0.5 * chi2, rtol=1e-14)
+    idx = np.random.default_rng(0).permutation(B)
+    assert np.array_equal(g.lnlhood_batch(U[idx], unit_cube=True), logl[idx])
+    P = g.prior_transform_batch(U[:4])
+    P[:, o.startind] = 0
+    cont = P[:, 1]
+    with np.errstate(all="ignore"):
+        expect = np.array([np.nansum((o.obj - c) ** 2 / o.obj_noise ** 2) for c in cont])
+    assert np.allclose(g.chi2_batch(P), expect, rtol=1e-6)
+    # spot-check 4 samples of the big batch against the oracle
+    Pq = g.prior_transform_batch(U[:4])
+    ref = np.array([o.lnlhood_worker(p) for p in Pq])
+    logl_close(logl[:4], ref, C)
