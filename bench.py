@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- batched Voigt-model logL evaluations per second (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Workload (BASELINE config 4): synthetic 8192-pixel spectrum, CIV doublet,
+20 components (40 Voigt lines per sample), floating spectral resolution and continuum, ndim 63;
+B unit-cube parameter vectors per GPU (default 262144, the top of the BASELINE sweep) drawn
+uniformly from the prior.  One step = one pass of the likelihood hot path over the batch.
+
+  value   whole-job logL/s with the parameter block already resident in HBM (device pointers,
+          CUDA events on the launching stream, max over ranks);
+  e2e     the same through the public host-buffer API (als_fitter.lnlhood_batch on pinned numpy
+          arrays): H2D of the parameters and D2H of logL inside the timed region;
+  roofline  FP32 ALU roofline of the fused kernel (this path is compute bound: SURVEY 8d):
+          executed FP32 flop/s of the kernel (per-path op counts x the kernel's own path
+          counters) over the FFMA peak measured in the same run;
+  cpu_baseline  the oracle port (numpy + scipy.special.wofz, the reference's algorithm) on the
+          host cores, bounded sample of the same parameter vectors.
+
+Multi-GPU (torchrun, one rank per GPU): the batch shards by sample, no exchange during the
+evaluation; every step ends with the logL gather over NCCL.  scaling = weak (B per GPU fixed).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+METRIC = "voigt_logL_evals_per_sec"
+UNIT = "logL/s"
+WORKLOAD = "cfg4: 8192 px x 20 comps x 2 lines (CIV doublet), free specres+continuum, ndim 63"
+
+# executed FP32 flops per unit of each path of mcalf_fast_kernel (FMA = 2, add/mul/min/max/rint = 1,
+# MUFU.RCP = 1); derivation in DESIGN.md section 5
+FLOP_WING = 16
+FLOP_MIXED = 17
+FLOP_CORE_EXTRA = 70
+FLOP_PIXEL = 33          # depth32 (23) + residual / chi-square (10); the stencil adds 2 per padded tap
+# SURVEY 8d canonical counts (Weideman-32 core, 3-term asymptotic wing)
+CANON_EVAL = 5.0
+CANON_CORE, CANON_WING = 242.0, 36.0
+
+
+def cfg4_spectrum():
+    from oracle import mcalf_oracle as orc   # inputs only (shared by tests and bench); not the measured path
+    return orc.config_kwargs(4, GOLDEN)
+
+
+def make_fitter(device):
+    import mcalf_b200
+    spec, kw = cfg4_spectrum()
+    return mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                                 **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                    if k not in ("fitrange", "fitlines", "ncomp")}, device=device)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU legs (oracle port; the only place bench.py executes oracle/ code as a workload)
+# ---------------------------------------------------------------------------------------------
+_CPU_FITTER = None
+
+
+def _cpu_init():
+    global _CPU_FITTER
+    from oracle import mcalf_oracle as orc
+    spec, kw = cfg4_spectrum()
+    _CPU_FITTER = orc.OracleFitter(spec, **kw)
+
+
+def _cpu_eval(U):
+    f = _CPU_FITTER
+    return [f.lnlhood_worker(f._scale_cube_pc(u)) for u in U]
+
+
+def cpu_pool():
+    import multiprocessing as mp
+    cores = len(os.sched_getaffinity(0))
+    pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+    pool.map(_cpu_eval, [np.zeros((0, 63))] * cores)   # every worker builds its fitter outside the timed region
+    return pool, cores
+
+
+def cpu_time(pool, cores, U):
+    chunks = [c for c in np.array_split(U, cores) if len(c)]
+    t0 = time.perf_counter()
+    pool.map(_cpu_eval, chunks)
+    return time.perf_counter() - t0
+
+
+def unit_cube(B, ndim, rank):
+    return np.random.default_rng(4000 + rank).random((B, ndim))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port: numpy + scipy wofz, every host
+    core) on a bounded sample of the same workload per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pool, cores = cpu_pool()
+    n = max(cores * 4, 64)
+    U = unit_cube(n, 63, 0)
+    for _ in range(args.warmup):
+        cpu_time(pool, cores, U[:cores])
+    t = sum(cpu_time(pool, cores, U) for _ in range(args.steps))
+    pool.close()
+    v = n * args.steps / t
+    sample = "%d prior-draw parameter vectors of the cfg-4 workload per step" % n
+    print(json.dumps({
+        "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch_per_step": n},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    g = make_fitter(local)
+    B, K, W = args.batch, args.steps, args.warmup
+    geo = g.geometry()
+
+    U_host = torch.from_numpy(unit_cube(B, g.ndim, rank)).pin_memory()
+    U_dev = U_host.cuda()
+    gathered = torch.empty(world * B, dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def step_device():
+        logl = g.lnlhood_batch(U_dev, unit_cube=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, logl)     # the logL gather over NVLink
+            return gathered
+        return logl
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(W):
+        out = step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    g.reset_stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        out = step_device()
+    e1.record()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    launches = g.stats()["kernel_launches"]
+    checksum = float(out.sum().item())
+
+    # ---- end to end through the host-buffer API ----
+    out_host = torch.empty(B, dtype=torch.float64).pin_memory()
+    Uh, Oh = U_host.numpy(), out_host.numpy()
+    import ctypes
+    from mcalf_b200 import capi
+
+    def step_host():
+        capi.check(g._lib.mcalf_loglike_batch(g._ctx, capi.ptr(Uh), B, g.ndim, capi.F_UNIT_CUBE, None, capi.ptr(Oh), None))
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out_host.cuda(non_blocking=True))
+
+    for _ in range(max(1, W // 2)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_host()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    clocks = sampler.stop() if rank == 0 else None
+    assert np.array_equal(Oh, out[rank * B:(rank + 1) * B].cpu().numpy()), "host and device paths disagree"
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    e2e_s = float(e2e_s.item())
+
+    if rank == 0:
+        # ---- roofline of the fused kernel: measured live, kernel alone on the stream ----
+        g.set_option("collect_stats", 1)
+        g.reset_stats()
+        g.lnlhood_batch(U_dev, unit_cube=True)
+        torch.cuda.synchronize()
+        st = g.stats()
+        g.set_option("collect_stats", 0)
+        kms = []
+        for _ in range(max(3, min(K, 10))):
+            g.lnlhood_batch(U_dev, unit_cube=True)
+            torch.cuda.synchronize()
+            kms.append(g.stats()["last_kernel_ms"])
+        kernel_ms = float(np.mean(kms))
+        P = g.prior_transform_batch(U_dev).cpu().numpy()
+        sig = P[:, 0] / 2.354820 / g.velstep
+        n = np.where(P[:, 0] > g.velstep, np.ceil(3.0348 * sig), 0)
+        taps_padded = 2 * (4 * np.ceil(n / 4)) + 4
+        npix = g.obj_wl.size
+        flop = (FLOP_WING * st["evals_wing"] + FLOP_MIXED * st["evals_mixed"] + FLOP_CORE_EXTRA * st["evals_core"]
+                + npix * (FLOP_PIXEL * B + 2.0 * taps_padded.sum()))
+        f_core_canon = 2.0 * math.sqrt(111.0) * np.mean(P[:, 5::3][:, :20]) / g.velstep / npix   # SURVEY 8d estimate
+        canon = (st["evals_total"] * (CANON_EVAL + f_core_canon * CANON_CORE + (1 - f_core_canon) * CANON_WING)
+                 + npix * (8.0 * B + 2.0 * (2 * n + 1).sum()))
+        peak_meas = capi.ffma_peak(local)
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        except (OSError, ValueError):
+            sm_max = 1965.0
+        peak_nominal = geo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
+        achieved = flop / (kernel_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp32_alu", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
+            "traffic": None,
+            "peak_source": "FFMA-only microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry)",
+            "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
+            "kernel": "mcalf_fast_kernel", "kernel_ms": kernel_ms, "flop_per_logL": flop / B,
+            "evals_per_logL": st["evals_total"] / B, "frac_wing": st["evals_wing"] / st["evals_total"],
+            "frac_mixed": st["evals_mixed"] / st["evals_total"], "frac_core": st["evals_core"] / st["evals_total"],
+            "canonical_flop_per_logL": canon / B, "canonical_tflops": canon / (kernel_ms * 1e-3) / 1e12,
+            "canonical_frac_of_nominal": canon / (kernel_ms * 1e-3) / 1e12 / peak_nominal,
+            "hbm_bytes_per_logL": g.ndim * 8 + 8,
+        }
+        # ---- CPU baseline: oracle port on the host cores, bounded sample of the same vectors ----
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            pool, cores = cpu_pool()
+            ncpu = max(cores * 4, 64)
+            tcpu = cpu_time(pool, cores, Uh[:ncpu])
+            pool.close()
+            cpu = {"value": ncpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": "first %d parameter vectors of the timed batch, multiprocessing.Pool(%d), oracle port "
+                             "(numpy + scipy.special.wofz)" % (ncpu, cores)}
+        total = world * B * K
+        line = {
+            "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B,
+                       "l2_policy": "inputs larger than L2 (%.0f MB parameter block per step)" % (B * g.ndim * 8 / 1e6),
+                       "cta_threads": geo["threads"], "ctas_per_sm": geo["ctas_per_sm"], "checksum": checksum,
+                       "parallelism": "sample-sharded x%d, logL all-gather" % world},
+            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": B * g.ndim * 8, "d2h_bytes_per_step": B * 8},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=262144, help="parameter vectors per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcalf_b200.so")
 SOURCES = ["mcalf_kernels.cu", "mcalf_api.cu"]
-HEADERS = ["mcalf_device.h", "voigt_math.cuh", "voigt_tables.inc", os.path.join("..", "..", "include", "mcalf_b200.h")]
+HEADERS = ["mcalf_device.h", "host_setup.h", "voigt_math.cuh", "voigt_tables.inc", os.path.join("..", "..", "include", "mcalf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC"]
 

@@ -1,0 +1,61 @@
+// host_setup.h -- the once-per-problem pixel layout of the fp32 kernel, plain C++ (no CUDA) so that
+// the C-ABI (mcalf_api.cu) and the host emulation used by the CPU tests build the same tables.
+#pragma once
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+namespace mcalf {
+
+// <= 256 consecutive pixels of the concatenated fit-window array sharing one fp64 reference rho_s
+struct ChunkDesc {
+    int start, len;
+    float dmin, dmax;     // range of delta = rho - rho_s over the chunk (slightly widened)
+    double rho_s;
+};
+
+constexpr int CHUNK_PIXELS = 256;
+constexpr double CHUNK_RHO_SPAN = 1.0 / 512.0;
+
+// Chunks: consecutive pixels whose rho = lam_ref/lambda spans at most CHUNK_RHO_SPAN (so that the fp32
+// offset delta = rho - rho_s keeps ~2^-34 absolute accuracy; fit-window gaps and non-uniform grids
+// simply start a new chunk), and delta as a two-float per pixel.
+inline void build_chunks(const double *wave, int npix, double lam_ref, std::vector<ChunkDesc> &chunks,
+                         std::vector<float> &dhi, std::vector<float> &dlo) {
+    chunks.clear();
+    dhi.assign(npix, 0.0f);
+    dlo.assign(npix, 0.0f);
+    int start = 0;
+    while (start < npix) {
+        double rmin = lam_ref / wave[start], rmax = rmin;
+        int len = 1;
+        while (start + len < npix && len < CHUNK_PIXELS) {
+            const double r = lam_ref / wave[start + len];
+            const double nmin = std::min(rmin, r), nmx = std::max(rmax, r);
+            if (nmx - nmin > CHUNK_RHO_SPAN) break;
+            rmin = nmin;
+            rmax = nmx;
+            ++len;
+        }
+        ChunkDesc cd;
+        cd.start = start;
+        cd.len = len;
+        cd.rho_s = 0.5 * (rmin + rmax);
+        float dmin = 3e38f, dmax = -3e38f;
+        for (int i = start; i < start + len; ++i) {
+            const double d = lam_ref / wave[i] - cd.rho_s;
+            dhi[i] = (float)d;
+            dlo[i] = (float)(d - (double)dhi[i]);
+            dmin = std::min(dmin, dhi[i]);
+            dmax = std::max(dmax, dhi[i]);
+        }
+        // widened a little so the classification bound also covers the dropped low part
+        cd.dmin = dmin - fabsf(dmin) * 1e-6f - 1e-12f;
+        cd.dmax = dmax + fabsf(dmax) * 1e-6f + 1e-12f;
+        chunks.push_back(cd);
+        start += len;
+    }
+}
+
+}  // namespace mcalf

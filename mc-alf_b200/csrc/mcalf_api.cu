@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "mcalf_device.h"
+#include "host_setup.h"
 
 using namespace mcalf;
 
@@ -149,6 +150,17 @@ int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_by
     return MCALF_OK;
 }
 
+// true when `p` is page-locked host memory the copy engines can reach directly
+bool is_pinned(const void *p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 // enqueue the kernels of one slice on `st`; all pointers are device pointers
 int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long long n, long long ld, uint32_t flags,
             double *d_logl, double *d_chi2, void *d_flux) {
@@ -213,14 +225,17 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     if (flux) slice = std::max<long long>(1, std::min<long long>(slice, (long long)((64u << 20) / ((size_t)c->P.npix * esize))));
     slice = std::min(slice, B);
     const size_t flux_bytes = flux ? (size_t)slice * c->P.npix * esize : 0;
+    // caller buffers that are already page-locked (mcalf_host_alloc, torch pin_memory) skip the staging copy
+    const bool pin_in = is_pinned(params);
+    const bool pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2), pin_flux = is_pinned(flux);
     struct Pending { long long off = 0, n = 0; bool live = false; } pend[NBUF];
     auto drain = [&](int k) -> int {
         Slot &s = c->slot[k];
         if (!pend[k].live) return MCALF_OK;
         CU(cudaEventSynchronize(s.done));
-        if (logl) memcpy(logl + pend[k].off, s.h_out, sizeof(double) * (size_t)pend[k].n);
-        if (chi2) memcpy(chi2 + pend[k].off, s.h_out + pend[k].n, sizeof(double) * (size_t)pend[k].n);
-        if (flux) memcpy((char *)flux + (size_t)pend[k].off * c->P.npix * esize, s.h_flux, (size_t)pend[k].n * c->P.npix * esize);
+        if (logl && !pin_logl) memcpy(logl + pend[k].off, s.h_out, sizeof(double) * (size_t)pend[k].n);
+        if (chi2 && !pin_chi2) memcpy(chi2 + pend[k].off, s.h_out + pend[k].n, sizeof(double) * (size_t)pend[k].n);
+        if (flux && !pin_flux) memcpy((char *)flux + (size_t)pend[k].off * c->P.npix * esize, s.h_flux, (size_t)pend[k].n * c->P.npix * esize);
         pend[k].live = false;
         return MCALF_OK;
     };
@@ -232,12 +247,19 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         if (rc) return rc;
         rc = ensure_slot(c, s, slice, ld, flux_bytes, true);
         if (rc) return rc;
-        memcpy(s.h_params, params + off * ld, sizeof(double) * (size_t)n * (size_t)ld);
-        CU(cudaMemcpyAsync(s.d_params, s.h_params, sizeof(double) * (size_t)n * (size_t)ld, cudaMemcpyHostToDevice, s.stream));
-        rc = enqueue(c, s, s.stream, s.d_params, n, ld, flags, s.d_out, s.d_out + n, flux ? s.d_flux : nullptr);
+        const double *src = params + off * ld;
+        if (!pin_in) {
+            memcpy(s.h_params, src, sizeof(double) * (size_t)n * (size_t)ld);
+            src = s.h_params;
+        }
+        CU(cudaMemcpyAsync(s.d_params, src, sizeof(double) * (size_t)n * (size_t)ld, cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue(c, s, s.stream, s.d_params, n, ld, flags, logl ? s.d_out : nullptr, chi2 ? s.d_out + n : nullptr,
+                     flux ? s.d_flux : nullptr);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
-        if (flux) CU(cudaMemcpyAsync(s.h_flux, s.d_flux, (size_t)n * c->P.npix * esize, cudaMemcpyDeviceToHost, s.stream));
+        if (logl) CU(cudaMemcpyAsync(pin_logl ? logl + off : s.h_out, s.d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        if (chi2) CU(cudaMemcpyAsync(pin_chi2 ? chi2 + off : s.h_out + n, s.d_out + n, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, s.stream));
+        if (flux) CU(cudaMemcpyAsync(pin_flux ? (void *)((char *)flux + (size_t)off * c->P.npix * esize) : s.h_flux, s.d_flux,
+                                     (size_t)n * c->P.npix * esize, cudaMemcpyDeviceToHost, s.stream));
         CU(cudaEventRecord(s.done, s.stream));
         pend[k].off = off;
         pend[k].n = n;
@@ -347,41 +369,9 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     }
     P.logC = -0.5 * csum;
 
-    // chunks: <= 256 consecutive pixels whose rho = lam_ref/lambda spans at most 2^-9
     std::vector<ChunkDesc> chunks;
-    std::vector<float> dhi(npix), dlo(npix);
-    {
-        int start = 0;
-        while (start < npix) {
-            double rmin = P.lam_ref / wave[start], rmax = rmin;
-            int len = 1;
-            while (start + len < npix && len < 256) {
-                const double r = P.lam_ref / wave[start + len];
-                const double nmin = std::min(rmin, r), nmx = std::max(rmax, r);
-                if (nmx - nmin > 1.0 / 512.0) break;
-                rmin = nmin;
-                rmax = nmx;
-                ++len;
-            }
-            ChunkDesc cd;
-            cd.start = start;
-            cd.len = len;
-            cd.rho_s = 0.5 * (rmin + rmax);
-            float dmin = 3e38f, dmax = -3e38f;
-            for (int i = start; i < start + len; ++i) {
-                const double d = P.lam_ref / wave[i] - cd.rho_s;
-                dhi[i] = (float)d;
-                dlo[i] = (float)(d - (double)dhi[i]);
-                dmin = std::min(dmin, dhi[i]);
-                dmax = std::max(dmax, dhi[i]);
-            }
-            // widen by one ulp-ish so the classification bound covers the dropped low part
-            cd.dmin = dmin - fabsf(dmin) * 1e-6f - 1e-12f;
-            cd.dmax = dmax + fabsf(dmax) * 1e-6f + 1e-12f;
-            chunks.push_back(cd);
-            start += len;
-        }
-    }
+    std::vector<float> dhi, dlo;
+    build_chunks(wave.data(), npix, P.lam_ref, chunks, dhi, dlo);
     P.nchunks = (int)chunks.size();
 
     std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),

@@ -5,15 +5,9 @@
 #include <stdint.h>
 
 #include "../../include/mcalf_b200.h"
+#include "host_setup.h"
 
 namespace mcalf {
-
-// <= 256 consecutive pixels of the concatenated fit-window array sharing one fp64 reference rho_s
-struct ChunkDesc {
-    int start, len;
-    float dmin, dmax;     // range of delta = rho - rho_s over the chunk
-    double rho_s;
-};
 
 // Everything als_fitter.__init__ leaves behind (hires_fitter.py:65-200), in device form.
 struct DevProblem {

@@ -108,6 +108,19 @@ class als_fitter:
                  brange=[1, 30], zrange=None, Nrangefill=[11.5, 16], brangefill=[1, 30], wrangefill=None,
                  coldef=['Wave', 'Flux', 'Err'], Gpriors=None, Asymmlike=False, debug=False, *,
                  device=None, precision="fp32", gauss_cdf=None, atomic=None):
+        self._init_host(specfile, fitrange, fitlines, ncomp, nfill, specres, contval, Nrange, brange, zrange,
+                        Nrangefill, brangefill, wrangefill, coldef, Gpriors, Asymmlike, debug, precision=precision,
+                        gauss_cdf=gauss_cdf, atomic=atomic)
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        self.device = int(device)
+        self._create_context()
+
+    def _init_host(self, specfile, fitrange, fitlines, ncomp, nfill=0, specres=[7.0], contval=[1.0], Nrange=[11.5, 16],
+                   brange=[1, 30], zrange=None, Nrangefill=[11.5, 16], brangefill=[1, 30], wrangefill=None,
+                   coldef=['Wave', 'Flux', 'Err'], Gpriors=None, Asymmlike=False, debug=False, *,
+                   precision="fp32", gauss_cdf=None, atomic=None):
+        """The once-per-run host part of the reference constructor (hires_fitter.py:32-200)."""
         self.debug = debug
         self.specfile = specfile
         self.fitrange = fitrange
@@ -224,11 +237,6 @@ class als_fitter:
         self._blo = np.array([np.min(b) for b in self.bounds], dtype=np.float64)
         self._bhi = np.array([np.max(b) for b in self.bounds], dtype=np.float64)
         self._ptp = self._bhi - self._blo
-
-        if device is None:
-            device = int(os.environ.get("LOCAL_RANK", "0"))
-        self.device = int(device)
-        self._create_context()
 
     # ------------------------------------------------------------------------------------------
     # context

@@ -1,5 +1,12 @@
-// TEST INFRASTRUCTURE: host build of mc-alf_b200/csrc/voigt_math.cuh so the kernels' arithmetic can
-// be checked against scipy.special.wofz without a GPU.  Never linked into the product library.
+// TEST INFRASTRUCTURE: host build of the device arithmetic in mc-alf_b200/csrc/voigt_math.cuh and of
+// the per-sample algorithm of mcalf_fast_kernel (same functions, same order of operations), so the
+// numerics can be checked against scipy / the oracle without a GPU.  Never linked into the product
+// library and never used to produce a result the product returns.
+#include <math.h>
+
+#include <vector>
+
+#include "host_setup.h"
 #include "voigt_math.cuh"
 
 using namespace mcalf;
@@ -18,54 +25,90 @@ void emul_exp_neg32(long n, const double *x, double *out) {
     for (long i = 0; i < n; ++i) out[i] = (double)exp_neg32((float)x[i], 0.0f);
 }
 
-// tau of one line over a pixel grid exactly as the fp32 kernel computes it.
-// mode 0: near form everywhere (two-float coordinate + core fix-up); mode 1: far form everywhere
-// (one FMA, wing only); mode 2: the kernel's own per-256-pixel-segment choice.
-// d_near_out receives the line's near/far switch distance in rho units.
-void emul_line_tau(long npix, const double *wave, double lam_ref, double logN, double z, double b, double wrest,
-                   double f, double gamma, int mode, double eps_far, double *tau_out, double *u_out,
-                   double *d_near_out) {
-    Line64 L64 = line_setup64(logN, z, b, wrest, f, gamma, lam_ref);
-    Line32 L = line_setup32(L64, eps_far, 0.0);
-    *d_near_out = L.d_near;
-    for (long s0 = 0; s0 < npix; s0 += 256) {
-        long s1 = s0 + 256 < npix ? s0 + 256 : npix;
-        float rmin = 3e38f, rmax = -3e38f;
-        for (long i = s0; i < s1; ++i) {
-            float r = (float)(lam_ref / wave[i]);
-            rmin = fminf(rmin, r);
-            rmax = fmaxf(rmax, r);
-        }
-        float dist = fmaxf(fmaxf(rmin - L.rc_hi, L.rc_hi - rmax), 0.0f);
-        bool far = mode == 1 || (mode == 2 && dist > L.d_near);
-        for (long i = s0; i < s1; ++i) {
-            float hi, lo;
-            split2(lam_ref / wave[i], hi, lo);
-            float tau;
-            if (far) {
-                float u = fma32(L.A_hi, hi, L.U0);
-                float s = fma32(u, u, L.a2);
-                s = fmaxf(s, S_CUT);
-                tau = L.c1 * wing_qp(s);
-                u_out[i] = u;
-            } else {
-                float dh = hi - L.rc_hi, dl = lo - L.rc_lo;
-                float t = dh + dl;
-                float u = L.A_hi * t;
-                float s = fma32(u, u, L.a2);
-                float sc = fmaxf(s, S_CUT);
-                tau = L.c1 * wing_qp(sc);
-                u_out[i] = u;
-                if (s < S_CUT) {
-                    float e = dl - (t - dh);
-                    float ul = fma32(L.A_hi, t, -u) + fma32(L.A_hi, e, L.A_lo * t);
-                    tau += fma32(L.kappa, core_h32(L.a, L.a2, u, ul), -L.c1w);
-                }
-            }
-            tau_out[i] = tau;
-        }
-    }
+void emul_depth32(long n, const double *x, double *out) {
+    for (long i = 0; i < n; ++i) out[i] = (double)depth32((float)x[i]);
 }
 
 void emul_lsf_geometry(double fwhm, double velstep, double *sigma_px, int *n) { lsf_geometry(fwhm, velstep, *sigma_px, *n); }
+
+int emul_num_chunks(long npix, const double *wave) {
+    std::vector<ChunkDesc> chunks;
+    std::vector<float> dhi, dlo;
+    build_chunks(wave, (int)npix, wave[npix / 2], chunks, dhi, dlo);
+    return (int)chunks.size();
 }
+
+// Optical depth of `nlines` lines over the pixel grid exactly as mcalf_fast_kernel accumulates it
+// (chunk classification, one-FMA wing coordinate, two-float core coordinate).  lines: rows of
+// (logN, z, b_kms, wrest, f, gamma).  cls_out (nullable): [nchunks*nlines] class of each pair.
+void emul_tau(long npix, const double *wave, int nlines, const double *lines, double eps_cull, double *tau_out,
+              int *cls_out) {
+    const double lam_ref = wave[npix / 2];
+    std::vector<ChunkDesc> chunks;
+    std::vector<float> dhi, dlo;
+    build_chunks(wave, (int)npix, lam_ref, chunks, dhi, dlo);
+    std::vector<float> tau(npix, 0.0f);
+    for (size_t c = 0; c < chunks.size(); ++c) {
+        const ChunkDesc &cd = chunks[c];
+        // the kernel sums wing-only lines first, then the mixed ones
+        for (int pass = 1; pass <= 2; ++pass) {
+            for (int t = 0; t < nlines; ++t) {
+                const double *l = lines + 6 * t;
+                const Line64 L64 = line_setup64(l[0], l[1], l[2], l[3], l[4], l[5], lam_ref);
+                const LineP L = line_pack(L64);
+                const double U = L64.A * (cd.rho_s - L64.rc);
+                float Uh, Ul;
+                split2(U, Uh, Ul);
+                const int cls = chunk_class(L.A_hi, Uh, cd.dmin, cd.dmax, L.c1, (float)eps_cull);
+                if (cls_out && pass == 1) cls_out[c * nlines + t] = cls;
+                if (cls != pass) continue;
+                for (int i = cd.start; i < cd.start + cd.len; ++i) {
+                    if (cls == 1) {
+                        const float u = fma32(L.A_hi, dhi[i], Uh);
+                        const float s = fma32(u, u, L.a2);
+                        tau[i] += wing_tau(L.c1, s);
+                    } else {
+                        bool core;
+                        tau[i] += mixed_tau(L, Uh, Ul, dhi[i], dlo[i], core);
+                    }
+                }
+            }
+        }
+    }
+    for (long i = 0; i < npix; ++i) tau_out[i] = (double)tau[i];
+}
+
+// Depth -> LSF stencil -> model and chi-square with the kernel's fp32 arithmetic.
+// pix: obj (0 where dropped), w (0 where dropped).  Returns chi2; model_out[npix] as double.
+double emul_epilogue(long npix, const double *tau, const double *obj, const double *w, double specres, double velstep,
+                     double cont, double *model_out) {
+    int n = 0;
+    double sigma = 1.0;
+    const bool conv = specres > velstep;
+    if (conv) lsf_geometry(specres, velstep, sigma, n);
+    const double inv2s2 = conv ? 0.5 / (sigma * sigma) : 0.0;
+    double norm = 0.0;
+    for (int k = 0; k <= n; ++k) norm += (k == 0 ? 1.0 : 2.0) * exp(-(double)(k * k) * inv2s2);
+    norm = 1.0 / norm;
+    std::vector<float> g(2 * n + 1), dep(npix);
+    for (int k = -n; k <= n; ++k) g[k + n] = (float)(exp(-(double)(k * k) * inv2s2) * norm);
+    for (long i = 0; i < npix; ++i) dep[i] = depth32((float)tau[i]);
+    const float c_hi = (float)cont, c_lo = (float)(cont - (double)c_hi);
+    double chi2 = 0.0;
+    for (long i = 0; i < npix; ++i) {
+        float s = 0.0f;
+        for (int k = -n; k <= n; ++k) {
+            long j = (i + k) % npix;
+            if (j < 0) j += npix;
+            s = fma32(g[k + n], dep[j], s);
+        }
+        const float oh = (float)obj[i], ol = (float)(obj[i] - (double)oh);
+        const float base = (oh - c_hi) + (ol - c_lo);
+        const float res = fma32(c_hi, s, base) + c_lo * s;
+        chi2 += (double)((float)w[i] * res * res);
+        model_out[i] = cont - cont * (double)s;
+    }
+    return chi2;
+}
+
+}  // extern "C"
