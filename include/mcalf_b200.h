@@ -77,12 +77,14 @@ typedef struct mcalf_stats {
     uint64_t kernel_launches;  /* CUDA kernels this library launched                                    */
     uint64_t samples;          /* parameter vectors evaluated                                           */
     uint64_t samples_fp64;     /* ... of which by the fp64 kernel (MCALF_F_FP64, or re-routed: a > a_max) */
-    /* the next five only advance while option "collect_stats" is 1 (fp32 kernel)                       */
+    /* the next seven only advance while option "collect_stats" is 1 (fp32 kernel)                       */
     uint64_t evals_total;      /* (line, pixel) Voigt evaluations the reference would perform           */
     uint64_t evals_wing;       /* ... in (line, chunk) pairs served by the wing-only form               */
     uint64_t evals_mixed;      /* ... in pairs that may contain line-core pixels                        */
     uint64_t evals_core;       /* ... of the mixed ones that took the line-core branch                  */
     uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound                     */
+    uint64_t evals_far;        /* ... in pairs folded into the chunk's far-field polynomial             */
+    uint64_t far_chunks;       /* (sample, chunk) pairs that evaluated a far-field polynomial           */
     double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events)            */
 } mcalf_stats_t;
 
@@ -118,6 +120,8 @@ int mcalf_get_stats(mcalf_ctx *ctx, mcalf_stats_t *out);
 int mcalf_reset_stats(mcalf_ctx *ctx);
 /* Options: "cull_eps"  (line, chunk) pairs whose optical depth is provably below it are skipped
  *                      (default 0 = never: the reference never skips);
+ *          "far_eps"   optical-depth error allowed to a (line, chunk) pair that is folded into the
+ *                      chunk's far-field expansion of the Lorentzian wings (default 1e-9; 0 = never);
  *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default and
  *                      upper limit 0.02: the validity range of the fp32 line-core series);
  *          "collect_stats" 0/1; "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);

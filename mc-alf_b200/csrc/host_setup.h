@@ -11,7 +11,7 @@ namespace mcalf {
 // <= 256 consecutive pixels of the concatenated fit-window array sharing one fp64 reference rho_s
 struct ChunkDesc {
     int start, len;
-    float dmin, dmax;     // range of delta = rho - rho_s over the chunk (slightly widened)
+    float ds, inv_ds;     // max |delta| over the chunk (slightly widened), delta = rho - rho_s, and 1/ds
     double rho_s;
 };
 
@@ -51,8 +51,8 @@ inline void build_chunks(const double *wave, int npix, double lam_ref, std::vect
             dmax = std::max(dmax, dhi[i]);
         }
         // widened a little so the classification bound also covers the dropped low part
-        cd.dmin = dmin - fabsf(dmin) * 1e-6f - 1e-12f;
-        cd.dmax = dmax + fabsf(dmax) * 1e-6f + 1e-12f;
+        cd.ds = std::max(fabsf(dmin), fabsf(dmax)) * (1.0f + 1e-6f) + 1e-12f;
+        cd.inv_ds = 1.0f / cd.ds;
         chunks.push_back(cd);
         start += len;
     }

@@ -325,6 +325,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     P.asym_t4 = p->asym_thresh4;
     P.a_max = A_MAX_LIMIT;
     P.eps_cull = 0.0f;
+    P.eps_far = 1e-9f;
     P.Lmax = std::max(p->ncompmax * p->nlines + p->nfill, std::max(p->nlines, 1));
     P.lam_ref = p->wave[npix / 2];
     if (!(P.lam_ref > 0.0)) return fail(MCALF_E_INVALID, "non-positive wavelength");
@@ -518,6 +519,8 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     out->evals_mixed = h[2];
     out->evals_core = h[3];
     out->evals_culled = h[4];
+    out->evals_far = h[5];
+    out->far_chunks = h[6];
     if (c->last_slot >= 0) {
         float ms = 0.f;
         Slot &s = c->slot[c->last_slot];
@@ -541,6 +544,9 @@ int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
     if (!strcmp(name, "cull_eps")) {
         if (!(value >= 0.0)) return fail(MCALF_E_INVALID, "cull_eps must be >= 0");
         c->P.eps_cull = (float)value;
+    } else if (!strcmp(name, "far_eps")) {
+        if (!(value >= 0.0) || value > 1e-6) return fail(MCALF_E_INVALID, "far_eps must be in [0, 1e-6]");
+        c->P.eps_far = (float)value;
     } else if (!strcmp(name, "a_max")) {
         if (!(value >= 0.0) || value > A_MAX_LIMIT) return fail(MCALF_E_INVALID, "a_max must be in [0, %g]", A_MAX_LIMIT);
         c->P.a_max = value;
@@ -569,6 +575,7 @@ int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
 int mcalf_get_option(mcalf_ctx *c, const char *name, double *value) {
     if (!c || !name || !value) return fail(MCALF_E_INVALID, "null argument");
     if (!strcmp(name, "cull_eps")) *value = c->P.eps_cull;
+    else if (!strcmp(name, "far_eps")) *value = c->P.eps_far;
     else if (!strcmp(name, "a_max")) *value = c->P.a_max;
     else if (!strcmp(name, "collect_stats")) *value = c->collect_stats;
     else if (!strcmp(name, "threads")) *value = c->threads;

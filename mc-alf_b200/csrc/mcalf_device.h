@@ -16,7 +16,7 @@ struct DevProblem {
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
     int Lmax, pad_;
-    float eps_cull, padf_;
+    float eps_cull, eps_far;
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
@@ -38,7 +38,7 @@ struct BatchArgs {
     unsigned int *work_counter;         // zeroed before the launch
     unsigned int *fallback_count;       // zeroed before the launch
     int *fallback_list;                 // [B]
-    unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled} evaluations
+    unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far} evaluations, far chunks
 };
 
 size_t fast_smem_bytes(const DevProblem &P, int nwarps);

@@ -166,12 +166,12 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     const uint32_t flags = Bt.flags;
 
     // per-thread statistics (only summed when Bt.stats != nullptr)
-    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0;
+    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_farchunks = 0;
 
     for (;;) {
         // ---- next sample (dynamic: the active-component count varies per sample) ----
         __syncthreads();
-        if (tid == 0) S.misc[0] = (int)atomicAdd(Bt.work_counter, 1u);
+        if (tid == 0) { S.misc[0] = (int)atomicAdd(Bt.work_counter, 1u); S.misc[3] = 0; }
         __syncthreads();
         const long long b = S.misc[0];
         if (b >= Bt.B) break;
@@ -214,24 +214,35 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         float4 *roww = S.row_w + (size_t)warp * P.Lmax;
         float2 *rowu = S.row_u + (size_t)warp * P.Lmax;
         int *rowm = S.row_m + (size_t)warp * P.Lmax;
-        for (int c = warp; c < P.nchunks; c += nwarps) {
+        // chunks are handed out dynamically: a chunk holding several line cores costs many times one
+        // that sees only far lines, and the CTA's warps must meet at the barrier below
+        for (;;) {
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&S.misc[3], 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= P.nchunks) break;
             const ChunkDesc cd = P.chunks[c];
             // (line, chunk) offsets U = A (rho_s - rho_c) in fp64, classification, compaction
-            int nw = 0, nm = 0;
+            int nw = 0, nm = 0, nf = 0;
+            float C[FF_DEG + 1];
+#pragma unroll
+            for (int n = 0; n <= FF_DEG; ++n) C[n] = 0.0f;
             for (int t0 = 0; t0 < h.nact; t0 += 32) {
                 const int t = t0 + lane;
-                int cls = 0;
+                int cls = -1;
                 float Uh = 0.f, Ul = 0.f;
                 LineP L;
                 if (t < h.nact) {
                     const double U = S.A64[t] * (cd.rho_s - S.rc64[t]);
                     split2(U, Uh, Ul);
                     L = S.lp[t];
-                    cls = chunk_class(L.A_hi, Uh, cd.dmin, cd.dmax, L.c1, P.eps_cull);
+                    cls = chunk_class(L.A_hi, Uh, cd.ds, L.c1, P.eps_cull, P.eps_far);
                     if (cls == 0) st_cull += cd.len;
+                    if (cls == 3) farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C);
                 }
                 const unsigned mw = __ballot_sync(0xffffffffu, cls == 1);
                 const unsigned mm = __ballot_sync(0xffffffffu, cls == 2);
+                const unsigned mf = __ballot_sync(0xffffffffu, cls == 3);
                 const unsigned below = (1u << lane) - 1u;
                 if (cls == 1) roww[nw + __popc(mw & below)] = make_float4(Uh, L.A_hi, L.a2, L.c1);
                 if (cls == 2) {
@@ -241,6 +252,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 }
                 nw += __popc(mw);
                 nm += __popc(mm);
+                nf += __popc(mf);
             }
             __syncwarp();
 
@@ -250,6 +262,16 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 const int k = j * 32 + lane;
                 d[j] = (k < cd.len) ? __ldg(P.delta_hi + cd.start + k) : 0.0f;
                 tau[j] = 0.0f;
+            }
+            // far lines: their summed local expansion, one polynomial per pixel
+            if (nf) {
+#pragma unroll
+                for (int n = 0; n <= FF_DEG; ++n) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) C[n] += __shfl_xor_sync(0xffffffffu, C[n], o);
+                }
+#pragma unroll
+                for (int j = 0; j < PX; ++j) tau[j] = farfield_eval(C, d[j] * cd.inv_ds);
             }
             // wing-only lines: one LDS.128 per line, 8 evaluations per lane
             for (int e = 0; e < nw; ++e) {
@@ -286,6 +308,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 st_wing += (unsigned long long)nw * cd.len;
                 st_mixed += (unsigned long long)nm * cd.len;
                 st_total += (unsigned long long)h.nact * cd.len;
+                st_far += (unsigned long long)nf * cd.len;
+                st_farchunks += nf ? 1 : 0;
             }
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
@@ -346,13 +370,13 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const float base = (px.x - c_hi) + (px.y - c_lo);
                     const float res = fma32(c_hi, dep, base) + c_lo * dep;
                     part = fma32(px.z * res, res, part);
-                    const double md = h.cont - h.cont * (double)dep;
                     if (Bt.flux_out) {
+                        const double md = h.cont - h.cont * (double)dep;
                         if (flags & MCALF_F_FLUX_F64) ((double *)Bt.flux_out)[b * (long long)P.npix + o] = md;
                         else ((float *)Bt.flux_out)[b * (long long)P.npix + o] = (float)md;
                     }
                     if (P.asymmlike) {
-                        const double rs = (P.obj_raw[o] - md) * P.isig[o];
+                        const double rs = (P.obj_raw[o] - (h.cont - h.cont * (double)dep)) * P.isig[o];
                         cnt5 += rs > 5.0;
                         cnt4 += rs > 4.0;
                     }
@@ -390,12 +414,16 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         st_core = (unsigned long long)warp_sum((double)st_core);
         st_cull = (unsigned long long)warp_sum((double)st_cull);
         st_total = (unsigned long long)warp_sum((double)st_total);
+        st_far = (unsigned long long)warp_sum((double)st_far);
+        st_farchunks = (unsigned long long)warp_sum((double)st_farchunks);
         if (lane == 0) {
             atomicAdd(Bt.stats + 0, st_total);
             atomicAdd(Bt.stats + 1, st_wing);
             atomicAdd(Bt.stats + 2, st_mixed);
             atomicAdd(Bt.stats + 3, st_core);
             atomicAdd(Bt.stats + 4, st_cull);
+            atomicAdd(Bt.stats + 5, st_far);
+            atomicAdd(Bt.stats + 6, st_farchunks);
         }
     }
 }

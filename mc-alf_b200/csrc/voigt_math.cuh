@@ -263,16 +263,64 @@ MCALF_HD LineP line_pack(const Line64 &L) {
 // covers the one-FMA coordinate's error).
 constexpr float U_CORE_MARGIN = 6.01f;
 
-// Class of a (line, chunk) pair from the u range the chunk spans: 0 = culled, 1 = wing only,
-// 2 = mixed (some pixel may have u^2 + a^2 < S_CUT).
-MCALF_HD int chunk_class(float A_hi, float U_hi, float dmin, float dmax, float c1, float eps_cull) {
-    const float u1 = fma32(A_hi, dmin, U_hi), u2 = fma32(A_hi, dmax, U_hi);
-    const float lo = fminf(u1, u2), hi = fmaxf(u1, u2);
-    if (!(lo > U_CORE_MARGIN || hi < -U_CORE_MARGIN)) return 2;   // also catches NaN
-    const float m = fminf(fabsf(lo), fabsf(hi));
+// Far-field ("local expansion") of the Lorentzian wings.  For a line whose centre lies far outside a
+// chunk, tau(delta) = c1 g(U + A delta), g(u) = 1/u^2 + (3/2 - a^2)/u^4 + (15/4)/u^6 (the asymptotic
+// series of sqrt(pi) H/a), is expanded in x = delta/ds in [-1, 1] (ds = max |delta| of the chunk):
+//   1/u^(2m) = U^(-2m) sum_n binom(-2m, n) (r x)^n,   r = A ds / U,  |r| <= FF_RMAX,
+// truncated at degree FF_DEG.  All far lines of a chunk are summed into ONE polynomial, evaluated once
+// per pixel.  A (line, chunk) pair takes this form only if the proven error bound
+//   c1/umin^2 [ 2 (FF_DEG+2) r^(FF_DEG+1)/(1-FF_RMAX)^2 + 14/umin^6 ] <= eps_far
+// holds (umin = |U| - A ds, the closest approach), so strong or nearby lines stay on the direct form.
+constexpr int FF_DEG = 5;
+constexpr float FF_RMAX = 0.45f;
+constexpr float FF_UMIN = 10.0f;
+constexpr float FF_TRUNC = 2.0f * (FF_DEG + 2) / ((1.0f - 0.45f) * (1.0f - 0.45f));
+
+// Class of a (line, chunk) pair: 0 = culled, 1 = wing only, 2 = mixed (some pixel may have
+// u^2 + a^2 < S_CUT), 3 = far field.  ds = max |delta| over the chunk.
+MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float eps_cull, float eps_far) {
+    const float hw = A_hi * ds;                  // half-width of the chunk in u
+    const float aU = fabsf(U_hi);
+    const float umin = aU - hw;
+    if (!(umin > U_CORE_MARGIN)) return 2;       // also catches NaN
+    const float um2 = umin * umin;
     // tau <= c1 q P(q) <= 1.05 c1 / u^2 on the chunk
-    if (1.05f * c1 < eps_cull * m * m) return 0;
+    if (1.05f * c1 < eps_cull * um2) return 0;
+    const float r = hw * rcp32(aU);
+    if (r <= FF_RMAX && umin >= FF_UMIN) {
+        const float r2 = r * r;
+        const float iu2 = rcp32(um2);
+        const float err = c1 * iu2 * fma32(FF_TRUNC, r2 * r2 * r2, 14.0f * iu2 * iu2 * iu2);
+        if (err <= eps_far) return 3;
+    }
     return 1;
+}
+
+// Add one far line's expansion coefficients (in x = delta/ds) to C[0..FF_DEG].
+MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, float a2, float *C) {
+    const float iU = rcp32(U_hi);
+    const float s = -(A_hi * ds) * iU;           // -r (signed)
+    const float v = iU * iU;
+    const float T1 = c1 * v;
+    const float T2 = T1 * v * (1.5f - a2);
+    const float T3 = T1 * v * v * 3.75f;
+    // binom(-2,n) = (-1)^n (n+1), binom(-4,n) = (-1)^n C(n+3,3), binom(-6,n) = (-1)^n C(n+5,5)
+    const float b2[6] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f};
+    const float b3[6] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f};
+    float sn = 1.0f;
+#pragma unroll
+    for (int n = 0; n <= FF_DEG; ++n) {
+        const float t = fma32((float)(n + 1), T1, fma32(b2[n], T2, b3[n] * T3));
+        C[n] = fma32(sn, t, C[n]);
+        sn *= s;
+    }
+}
+
+MCALF_HD float farfield_eval(const float *C, float x) {
+    float p = C[FF_DEG];
+#pragma unroll
+    for (int n = FF_DEG - 1; n >= 0; --n) p = fma32(p, x, C[n]);
+    return p;
 }
 
 // one wing evaluation: tau contribution of a line at s = u^2 + a^2 >= S_CUT

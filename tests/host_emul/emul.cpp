@@ -41,8 +41,8 @@ int emul_num_chunks(long npix, const double *wave) {
 // Optical depth of `nlines` lines over the pixel grid exactly as mcalf_fast_kernel accumulates it
 // (chunk classification, one-FMA wing coordinate, two-float core coordinate).  lines: rows of
 // (logN, z, b_kms, wrest, f, gamma).  cls_out (nullable): [nchunks*nlines] class of each pair.
-void emul_tau(long npix, const double *wave, int nlines, const double *lines, double eps_cull, double *tau_out,
-              int *cls_out) {
+void emul_tau(long npix, const double *wave, int nlines, const double *lines, double eps_cull, double eps_far,
+              double *tau_out, int *cls_out) {
     const double lam_ref = wave[npix / 2];
     std::vector<ChunkDesc> chunks;
     std::vector<float> dhi, dlo;
@@ -50,8 +50,10 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
     std::vector<float> tau(npix, 0.0f);
     for (size_t c = 0; c < chunks.size(); ++c) {
         const ChunkDesc &cd = chunks[c];
-        // the kernel sums wing-only lines first, then the mixed ones
-        for (int pass = 1; pass <= 2; ++pass) {
+        // the kernel evaluates the far-field polynomial first, then the wing-only lines, then the mixed ones
+        float C[FF_DEG + 1] = {0};
+        int nf = 0;
+        for (int pass = 0; pass <= 2; ++pass) {
             for (int t = 0; t < nlines; ++t) {
                 const double *l = lines + 6 * t;
                 const Line64 L64 = line_setup64(l[0], l[1], l[2], l[3], l[4], l[5], lam_ref);
@@ -59,8 +61,12 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
                 const double U = L64.A * (cd.rho_s - L64.rc);
                 float Uh, Ul;
                 split2(U, Uh, Ul);
-                const int cls = chunk_class(L.A_hi, Uh, cd.dmin, cd.dmax, L.c1, (float)eps_cull);
-                if (cls_out && pass == 1) cls_out[c * nlines + t] = cls;
+                const int cls = chunk_class(L.A_hi, Uh, cd.ds, L.c1, (float)eps_cull, (float)eps_far);
+                if (cls_out && pass == 0) cls_out[c * nlines + t] = cls;
+                if (pass == 0) {
+                    if (cls == 3) { farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C); ++nf; }
+                    continue;
+                }
                 if (cls != pass) continue;
                 for (int i = cd.start; i < cd.start + cd.len; ++i) {
                     if (cls == 1) {
@@ -73,6 +79,8 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
                     }
                 }
             }
+            if (pass == 0 && nf)
+                for (int i = cd.start; i < cd.start + cd.len; ++i) tau[i] = farfield_eval(C, dhi[i] * cd.inv_ds);
         }
     }
     for (long i = 0; i < npix; ++i) tau_out[i] = (double)tau[i];

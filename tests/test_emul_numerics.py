@@ -67,8 +67,9 @@ def _lines(o, p):
     return np.array(rows, dtype=np.float64).reshape(-1, 6)
 
 
+@pytest.mark.parametrize("far_eps", [0.0, 1e-9])
 @pytest.mark.parametrize("tag", ["cfg1", "cfg2", "cfg3", "cfg4", "edge_gap", "edge_strong"])
-def test_kernel_algorithm_on_host_vs_oracle(emul, tag, golden):
+def test_kernel_algorithm_on_host_vs_oracle(emul, tag, far_eps, golden):
     """Chunked classification + wing/core forms + depth stencil + two-float residual, run on the host:
     flux within 1e-6 of the continuum and logL within 1e-6 relative of the oracle."""
     spec, kw, extra = case(tag)
@@ -77,13 +78,16 @@ def test_kernel_algorithm_on_host_vs_oracle(emul, tag, golden):
     wave = np.ascontiguousarray(o.obj_wl)
     with np.errstate(all="ignore"):
         w = 1.0 / o.obj_noise ** 2
+    seen = set()
     for p in P:
         lines = _lines(o, p)
         tau = np.empty(wave.size)
         cls = np.zeros(emul.emul_num_chunks(ctypes.c_long(wave.size), wave.ctypes.data_as(dp)) * max(len(lines), 1), dtype=np.int32)
         emul.emul_tau(ctypes.c_long(wave.size), wave.ctypes.data_as(dp), len(lines), lines.ctypes.data_as(dp),
-                      ctypes.c_double(0.0), tau.ctypes.data_as(dp), cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
-        assert set(np.unique(cls)) <= {1, 2}            # nothing culled at cull_eps = 0
+                      ctypes.c_double(0.0), ctypes.c_double(far_eps), tau.ctypes.data_as(dp),
+                      cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+        assert set(np.unique(cls)) <= ({1, 2, 3} if far_eps else {1, 2})     # nothing culled at cull_eps = 0
+        seen |= set(np.unique(cls))
         res, cont, _ = o.unpack(p)
         model = np.empty(wave.size)
         chi2 = emul.emul_epilogue(ctypes.c_long(wave.size), tau.ctypes.data_as(dp), o.obj.ctypes.data_as(dp),
@@ -95,3 +99,5 @@ def test_kernel_algorithm_on_host_vs_oracle(emul, tag, golden):
         ref_logl = o.lnlhood_worker(p)
         const = ref_logl + 0.5 * ref_chi2
         assert abs((const - 0.5 * chi2) - ref_logl) <= 1e-6 * max(abs(ref_logl), abs(const))
+    if far_eps and tag in ("cfg3", "cfg4"):
+        assert 3 in seen          # the far-field form is actually exercised
