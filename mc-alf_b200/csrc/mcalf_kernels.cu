@@ -125,14 +125,33 @@ __device__ __forceinline__ int build_taps(const DevProblem &P, double specres, f
 // ---------------------------------------------------------------------------------------------
 constexpr int PX = 8;            // pixels per lane per chunk (chunk = 32 lanes x 8 = 256 pixels)
 
+// Rows (32 consecutive pixels) of chunk `cd` that the core |u| < U_CORE_MARGIN of a line can reach, from
+// the chunk's linear pixel <-> delta model; kslack (host computed) bounds the model's error in pixels.
+__device__ __forceinline__ void core_rows(const ChunkDesc &cd, float A_hi, float U_hi, int &j0, int &j1) {
+    const float iA = rcp32(A_hi);
+    const float ka = ((-U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
+    const float kb = ((U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
+    float lo = fminf(ka, kb) - (float)cd.kslack, hi = fmaxf(ka, kb) + (float)cd.kslack;
+    lo = fmaxf(lo, 0.0f);
+    hi = fminf(hi, (float)(cd.len - 1));
+    if (!(lo <= hi)) {                 // empty (or NaN): no row
+        j0 = 1;
+        j1 = 0;
+        if (!(lo == lo) || !(hi == hi)) { j0 = 0; j1 = PX - 1; }
+        return;
+    }
+    j0 = (int)lo >> 5;
+    j1 = (int)hi >> 5;
+}
+
 struct FastSmem {
     double *theta;     // [ndim_pad]
     double *A64;       // [Lmax]
     double *rc64;      // [Lmax]
     LineP *lp;         // [Lmax]
-    float4 *row_w;     // [nwarps][Lmax]  wing entries {U_hi, A_hi, a2, c1}
-    float2 *row_u;     // [nwarps][Lmax]  (U_hi, U_lo) of mixed entries
-    int *row_m;        // [nwarps][Lmax]  line index of mixed entries
+    float4 *row_w;     // [nwarps][Lmax]  direct-form entries {U_hi, A_hi, a2, c1}
+    float4 *row_c;     // [nwarps][Lmax]  core entries {line | row0 << 16 | row1 << 24, U_hi, U_lo, clamped wing value}
+    float *tcore;      // [nwarps][256]   per-warp core contributions of the current chunk
     float *taps;       // [2*nmax4 + 8]
     float *flux;       // [halo + npix4 + halo + 8]
     double *red;       // [64]
@@ -148,8 +167,8 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
     s.rc64 = (double *)take(sizeof(double) * P.Lmax);
     s.lp = (LineP *)take(sizeof(LineP) * P.Lmax);
     s.row_w = (float4 *)take(sizeof(float4) * P.Lmax * nwarps);
-    s.row_u = (float2 *)take(sizeof(float2) * P.Lmax * nwarps);
-    s.row_m = (int *)take(sizeof(int) * P.Lmax * nwarps);
+    s.row_c = (float4 *)take(sizeof(float4) * P.Lmax * nwarps);
+    s.tcore = (float *)take(sizeof(float) * PX * 32 * nwarps);
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
@@ -212,8 +231,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 
         // ---- synthesis: each warp owns chunks; tau stays in registers ----
         float4 *roww = S.row_w + (size_t)warp * P.Lmax;
-        float2 *rowu = S.row_u + (size_t)warp * P.Lmax;
-        int *rowm = S.row_m + (size_t)warp * P.Lmax;
+        float4 *rowc = S.row_c + (size_t)warp * P.Lmax;
+        float *tcore = S.tcore + warp * (PX * 32);
         // chunks are handed out dynamically: a chunk holding several line cores costs many times one
         // that sees only far lines, and the CTA's warps must meet at the barrier below
         for (;;) {
@@ -222,7 +241,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
             const ChunkDesc cd = P.chunks[c];
-            // (line, chunk) offsets U = A (rho_s - rho_c) in fp64, classification, compaction
+            // (line, chunk) offsets U = A (rho_s - rho_c) in fp64, classification, compaction.
+            // Lists: far lines fold into the polynomial C; every other line goes to the wing list
+            // (evaluated with s clamped at S_CUT); lines whose core may touch the chunk ALSO go to the
+            // core list with the range of 32-pixel rows their core can reach.
             int nw = 0, nm = 0, nf = 0;
             float C[FF_DEG + 1];
 #pragma unroll
@@ -240,15 +262,16 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     if (cls == 0) st_cull += cd.len;
                     if (cls == 3) farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C);
                 }
-                const unsigned mw = __ballot_sync(0xffffffffu, cls == 1);
+                const unsigned mw = __ballot_sync(0xffffffffu, cls == 1 || cls == 2);
                 const unsigned mm = __ballot_sync(0xffffffffu, cls == 2);
                 const unsigned mf = __ballot_sync(0xffffffffu, cls == 3);
                 const unsigned below = (1u << lane) - 1u;
-                if (cls == 1) roww[nw + __popc(mw & below)] = make_float4(Uh, L.A_hi, L.a2, L.c1);
+                if (cls == 1 || cls == 2) roww[nw + __popc(mw & below)] = make_float4(Uh, L.A_hi, L.a2, L.c1);
                 if (cls == 2) {
-                    const int k = nm + __popc(mm & below);
-                    rowu[k] = make_float2(Uh, Ul);
-                    rowm[k] = t;
+                    int j0, j1;
+                    core_rows(cd, L.A_hi, Uh, j0, j1);
+                    rowc[nm + __popc(mm & below)] =
+                        make_float4(__int_as_float(t | (j0 << 16) | (j1 << 24)), Uh, Ul, wing_tau(L.c1, S_CUT));
                 }
                 nw += __popc(mw);
                 nm += __popc(mm);
@@ -273,39 +296,70 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < PX; ++j) tau[j] = farfield_eval(C, d[j] * cd.inv_ds);
             }
-            // wing-only lines: one LDS.128 per line, 8 evaluations per lane
+            // direct wing form: one LDS.128 per line, 8 evaluations per lane; inside a line core the
+            // clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
             for (int e = 0; e < nw; ++e) {
                 const float4 L = roww[e];
 #pragma unroll
                 for (int j = 0; j < PX; ++j) {
                     const float u = fma32(L.y, d[j], L.x);
-                    const float s = fma32(u, u, L.z);
+                    const float s = fmaxf(fma32(u, u, L.z), S_CUT);
                     tau[j] += wing_tau(L.w, s);
                 }
             }
-            // lines whose core may fall in this chunk
-            for (int e = 0; e < nm; ++e) {
-                const int t = rowm[e];
-                const float2 U = rowu[e];
-                const LineP L = S.lp[t];
+            // line cores: only the 32-pixel rows a core can reach, accumulated in shared memory (the
+            // row index is dynamic, so the register-resident tau cannot be addressed here)
+            if (nm) {
 #pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    const float u = fma32(L.A_hi, d[j], U.x);
-                    const float s = fma32(u, u, L.a2);
-                    float v = wing_tau(L.c1, fmaxf(s, S_CUT));
-                    if (s < S_CUT) {
-                        const int k = j * 32 + lane;
-                        const float dlo = (k < cd.len) ? __ldg(P.delta_lo + cd.start + k) : 0.0f;
-                        float uh, ul;
-                        core_u2(L.A_hi, L.A_lo, d[j], dlo, U.x, U.y, uh, ul);
-                        v = L.kappa * core_h32(L.a, L.a2, uh, ul);
-                        if (Bt.stats) st_core += 1;
+                for (int j = 0; j < PX; ++j) tcore[j * 32 + lane] = 0.0f;
+                for (int e = 0; e < nm; ++e) {
+                    const float4 E = rowc[e];
+                    const int bits = __float_as_int(E.x);
+                    const int t = bits & 0xffff, j0 = (bits >> 16) & 0xff, j1 = (bits >> 24) & 0xff;
+                    const LineP L = S.lp[t];
+                    if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
+                        // branch-free, two rows in flight: the row loop is latency bound otherwise
+#pragma unroll 1
+                        for (int j = j0; j <= j1; j += 2) {
+                            const int ka = j * 32 + lane, kb = ka + 32;
+                            const bool va = ka < cd.len, vb = (j < j1) && (kb < cd.len);
+                            const int ia = cd.start + (va ? ka : 0), ib = cd.start + (vb ? kb : 0);
+                            const float dha = __ldg(P.delta_hi + ia), dla = __ldg(P.delta_lo + ia);
+                            const float dhb = __ldg(P.delta_hi + ib), dlb = __ldg(P.delta_lo + ib);
+                            const float ta = tcore[va ? ka : lane], tb = tcore[vb ? kb : lane];
+                            const float ua = fma32(L.A_hi, dha, E.y), ub = fma32(L.A_hi, dhb, E.y);
+                            const bool ca = va && fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
+                            const float uca = ua + fma32(L.A_hi, dla, fma32(L.A_lo, dha, E.z));
+                            const float ucb = ub + fma32(L.A_hi, dlb, fma32(L.A_lo, dhb, E.z));
+                            const float ha = core_h32_lean(L.a, L.a2, uca), hb = core_h32_lean(L.a, L.a2, ucb);
+                            if (ca) tcore[ka] = ta + fma32(L.kappa, ha, -E.w);
+                            if (cb) tcore[kb] = tb + fma32(L.kappa, hb, -E.w);
+                            if (Bt.stats) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
+                        }
+                    } else {
+#pragma unroll 1
+                        for (int j = j0; j <= j1; ++j) {
+                            const int k = j * 32 + lane;
+                            if (k < cd.len) {
+                                const float dh = __ldg(P.delta_hi + cd.start + k);
+                                const float u = fma32(L.A_hi, dh, E.y);
+                                const float s = fma32(u, u, L.a2);
+                                if (s < S_CUT) {
+                                    const float dl = __ldg(P.delta_lo + cd.start + k);
+                                    float uh, ul;
+                                    core_u2(L.A_hi, L.A_lo, dh, dl, E.y, E.z, uh, ul);
+                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -E.w);
+                                    if (Bt.stats) st_core += 1;
+                                }
+                            }
+                        }
                     }
-                    tau[j] += v;
                 }
+#pragma unroll
+                for (int j = 0; j < PX; ++j) tau[j] += tcore[j * 32 + lane];
             }
             if (Bt.stats && lane == 0) {
-                st_wing += (unsigned long long)nw * cd.len;
+                st_wing += (unsigned long long)(nw - nm) * cd.len;
                 st_mixed += (unsigned long long)nm * cd.len;
                 st_total += (unsigned long long)h.nact * cd.len;
                 st_far += (unsigned long long)nf * cd.len;
@@ -580,8 +634,8 @@ size_t fast_smem_bytes(const DevProblem &P, int nwarps) {
     take(sizeof(double) * P.Lmax);
     take(sizeof(LineP) * P.Lmax);
     take(sizeof(float4) * P.Lmax * nwarps);
-    take(sizeof(float2) * P.Lmax * nwarps);
-    take(sizeof(int) * P.Lmax * nwarps);
+    take(sizeof(float4) * P.Lmax * nwarps);
+    take(sizeof(float) * PX * 32 * nwarps);
     take(sizeof(float) * (2 * P.nmax4 + 8));
     take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     take(sizeof(double) * 64);

@@ -68,14 +68,24 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
                     continue;
                 }
                 if (cls != pass) continue;
+                // both classes: direct wing form with s clamped at S_CUT; class 2 then replaces the
+                // clamped value by the core form where s < S_CUT (as the kernel's core pass does)
+                const float c1w = wing_tau(L.c1, S_CUT);
                 for (int i = cd.start; i < cd.start + cd.len; ++i) {
-                    if (cls == 1) {
-                        const float u = fma32(L.A_hi, dhi[i], Uh);
-                        const float s = fma32(u, u, L.a2);
-                        tau[i] += wing_tau(L.c1, s);
-                    } else {
-                        bool core;
-                        tau[i] += mixed_tau(L, Uh, Ul, dhi[i], dlo[i], core);
+                    const float u = fma32(L.A_hi, dhi[i], Uh);
+                    const float s = fma32(u, u, L.a2);
+                    tau[i] += wing_tau(L.c1, fmaxf(s, S_CUT));
+                    if (cls == 2 && s < S_CUT) {
+                        float h;
+                        if (L.kappa <= KAPPA_LEAN) {
+                            const float uc = u + fma32(L.A_hi, dlo[i], fma32(L.A_lo, dhi[i], Ul));
+                            h = core_h32_lean(L.a, L.a2, uc);
+                        } else {
+                            float uh, ul;
+                            core_u2(L.A_hi, L.A_lo, dhi[i], dlo[i], Uh, Ul, uh, ul);
+                            h = core_h32(L.a, L.a2, uh, ul);
+                        }
+                        tau[i] += fma32(L.kappa, h, -c1w);
                     }
                 }
             }
