@@ -374,6 +374,14 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     std::vector<float> dhi, dlo;
     build_chunks(wave.data(), npix, P.lam_ref, chunks, dhi, dlo);
     P.nchunks = (int)chunks.size();
+    {   // pass-A geometry: lane groups of cslot_w chunks, 8 virtual warps
+        int w = 1, lw = 0;
+        while (w < 32 && w < P.nchunks) { w <<= 1; ++lw; }
+        P.cslot_w = w;
+        P.cslot_lw = lw;
+        P.nslots = 8 * (32 / w);
+        P.list_cap = (P.Lmax + P.nslots - 1) / P.nslots;
+    }
 
     std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),
         lg(p->line_gamma, p->line_gamma + p->nlines);

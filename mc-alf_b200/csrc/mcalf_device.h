@@ -15,7 +15,8 @@ struct DevProblem {
     int ncompmax, nfill, ndim, ndim_pad;
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
-    int Lmax, pad_;
+    int Lmax, list_cap;                 // list_cap: entries per (chunk, slot) sub-list
+    int cslot_w, cslot_lw, nslots, pad_; // lanes per chunk group (power of two), its log2, slots = 8 * 32 / cslot_w
     float eps_cull, eps_far;
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;

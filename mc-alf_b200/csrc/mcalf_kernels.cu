@@ -127,8 +127,7 @@ constexpr int PX = 8;            // pixels per lane per chunk (chunk = 32 lanes 
 
 // Rows (32 consecutive pixels) of chunk `cd` that the core |u| < U_CORE_MARGIN of a line can reach, from
 // the chunk's linear pixel <-> delta model; kslack (host computed) bounds the model's error in pixels.
-__device__ __forceinline__ void core_rows(const ChunkDesc &cd, float A_hi, float U_hi, int &j0, int &j1) {
-    const float iA = rcp32(A_hi);
+__device__ __forceinline__ void core_rows(const ChunkDesc &cd, float iA, float U_hi, int &j0, int &j1) {
     const float ka = ((-U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
     const float kb = ((U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
     float lo = fminf(ka, kb) - (float)cd.kslack, hi = fmaxf(ka, kb) + (float)cd.kslack;
@@ -144,21 +143,26 @@ __device__ __forceinline__ void core_rows(const ChunkDesc &cd, float A_hi, float
     j1 = (int)hi >> 5;
 }
 
+constexpr int FF_NC = FF_DEG + 1;
+constexpr int VWARPS = 8;        // virtual warps of the classification pass: fixes its summation and list
+                                 // order whatever the CTA size, so results do not depend on the launch geometry
+
 struct FastSmem {
     double *theta;     // [ndim_pad]
     double *A64;       // [Lmax]
     double *rc64;      // [Lmax]
     LineP *lp;         // [Lmax]
-    float4 *row_w;     // [nwarps][Lmax]  direct-form entries {U_hi, A_hi, a2, c1}
-    float4 *row_c;     // [nwarps][Lmax]  core entries {line | row0 << 16 | row1 << 24, U_hi, U_lo, clamped wing value}
-    float *tcore;      // [nwarps][256]   per-warp core contributions of the current chunk
+    int2 *wl;          // [nchunks][nslots][list_cap]  near lines of a chunk: {line | core << 16, U_hi bits}
+    float *farp;       // [nchunks][FF_NC * nslots + 1] partial far-field coefficients, [n][slot] within a chunk
+    int *cnt;          // [nchunks][nslots]            entries in each sub-list | core entries << 16
     float *taps;       // [2*nmax4 + 8]
     float *flux;       // [halo + npix4 + halo + 8]
     double *red;       // [64]
     int *misc;         // [8]
+    size_t bytes;
 };
 
-__device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem &P, int nwarps) {
+MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     FastSmem s;
     size_t o = 0;
     auto take = [&](size_t bytes) { unsigned char *p = base + o; o += (bytes + 15) & ~(size_t)15; return p; };
@@ -166,13 +170,14 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
     s.A64 = (double *)take(sizeof(double) * P.Lmax);
     s.rc64 = (double *)take(sizeof(double) * P.Lmax);
     s.lp = (LineP *)take(sizeof(LineP) * P.Lmax);
-    s.row_w = (float4 *)take(sizeof(float4) * P.Lmax * nwarps);
-    s.row_c = (float4 *)take(sizeof(float4) * P.Lmax * nwarps);
-    s.tcore = (float *)take(sizeof(float) * PX * 32 * nwarps);
+    s.wl = (int2 *)take(sizeof(int2) * (size_t)P.nchunks * P.nslots * P.list_cap);
+    s.farp = (float *)take(sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
+    s.cnt = (int *)take(sizeof(int) * (size_t)P.nchunks * P.nslots);
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
     s.misc = (int *)take(sizeof(int) * 8);
+    s.bytes = o;
     return s;
 }
 
@@ -181,11 +186,11 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-    FastSmem S = carve(smem_raw, P, nwarps);
+    FastSmem S = carve(smem_raw, P);
     const uint32_t flags = Bt.flags;
 
     // per-thread statistics (only summed when Bt.stats != nullptr)
-    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_farchunks = 0;
+    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0;
 
     for (;;) {
         // ---- next sample (dynamic: the active-component count varies per sample) ----
@@ -209,7 +214,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             const Line64 L = line_setup64(logN, z, bk, P.line_wrest[li], P.line_f[li], P.line_gamma[li], P.lam_ref);
             S.A64[t] = L.A;
             S.rc64[t] = L.rc;
-            S.lp[t] = line_pack(L);
+            S.lp[t] = line_pack_full(L);
             // outside the fp32 path's domain: damping too large, or anything non-finite / non-positive
             if (!(L.a <= P.a_max) || !(L.A > 0.0) || !(L.A < 1e30) || !(L.kappa < 1e30) || !(L.kappa >= 0.0)) bad = 1;
         }
@@ -229,10 +234,56 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         }
         n4 = S.misc[2];
 
-        // ---- synthesis: each warp owns chunks; tau stays in registers ----
-        float4 *roww = S.row_w + (size_t)warp * P.Lmax;
-        float4 *rowc = S.row_c + (size_t)warp * P.Lmax;
-        float *tcore = S.tcore + warp * (PX * 32);
+        // ---- pass A: classify every (line, chunk) pair, lane = chunk ----
+        // Far pairs fold into per-(chunk, slot) partial expansions, near pairs are listed per
+        // (chunk, slot).  A slot is one lane group of one of VWARPS virtual warps and owns the lines
+        // slot, slot + nslots, ...; sums and lists are later read in slot order.
+        {
+            const int W = P.cslot_w, LW = P.cslot_lw, SUB = 32 >> LW, NS = P.nslots, CAP = P.list_cap;
+            const int fstride = FF_NC * NS + 1;
+            for (int vw = warp; vw < VWARPS; vw += nwarps) {
+                const int slot = vw * SUB + (lane >> LW);
+                for (int cg = 0; cg < P.nchunks; cg += W) {
+                    const int c = cg + (lane & (W - 1));
+                    const bool cact = c < P.nchunks;
+                    const double rho_s = P.chunks[cact ? c : 0].rho_s;
+                    const float ds = P.chunks[cact ? c : 0].ds;
+                    float C[FF_NC];
+#pragma unroll
+                    for (int n = 0; n < FF_NC; ++n) C[n] = 0.0f;
+                    int nw = 0, nc = 0;
+                    int2 *list = S.wl + ((size_t)(cact ? c : 0) * NS + slot) * CAP;
+                    for (int t = slot; t < h.nact; t += NS) {
+                        const double U = S.A64[t] * (rho_s - S.rc64[t]);
+                        const float Uh = (float)U;
+                        const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
+                        const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, P.eps_cull, P.eps_far) : -1;
+                        if (cls == 3) farfield_accumulate(L.x, Uh, ds, L.z, L.y, C);
+                        if (cls == 1 || cls == 2) {
+                            list[nw++] = make_int2(t | (cls == 2 ? 0x10000 : 0), __float_as_int(Uh));
+                            nc += cls == 2;
+                        }
+                        if (Bt.stats) {
+                            const int len = cact ? P.chunks[c].len : 0;
+                            st_total += len;
+                            st_cull += cls == 0 ? len : 0;
+                            st_far += cls == 3 ? len : 0;
+                            st_wing += cls == 1 ? len : 0;
+                            st_mixed += cls == 2 ? len : 0;
+                        }
+                    }
+                    if (cact) {
+                        float *fp = S.farp + (size_t)c * fstride + slot;
+#pragma unroll
+                        for (int n = 0; n < FF_NC; ++n) fp[n * NS] = C[n];
+                        S.cnt[c * NS + slot] = nw | (nc << 16);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- pass B: synthesis, each warp takes chunks; tau stays in registers ----
         // chunks are handed out dynamically: a chunk holding several line cores costs many times one
         // that sees only far lines, and the CTA's warps must meet at the barrier below
         for (;;) {
@@ -241,129 +292,107 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
             const ChunkDesc cd = P.chunks[c];
-            // (line, chunk) offsets U = A (rho_s - rho_c) in fp64, classification, compaction.
-            // Lists: far lines fold into the polynomial C; every other line goes to the wing list
-            // (evaluated with s clamped at S_CUT); lines whose core may touch the chunk ALSO go to the
-            // core list with the range of 32-pixel rows their core can reach.
-            int nw = 0, nm = 0, nf = 0;
-            float C[FF_DEG + 1];
-#pragma unroll
-            for (int n = 0; n <= FF_DEG; ++n) C[n] = 0.0f;
-            for (int t0 = 0; t0 < h.nact; t0 += 32) {
-                const int t = t0 + lane;
-                int cls = -1;
-                float Uh = 0.f, Ul = 0.f;
-                LineP L;
-                if (t < h.nact) {
-                    const double U = S.A64[t] * (cd.rho_s - S.rc64[t]);
-                    split2(U, Uh, Ul);
-                    L = S.lp[t];
-                    cls = chunk_class(L.A_hi, Uh, cd.ds, L.c1, P.eps_cull, P.eps_far);
-                    if (cls == 0) st_cull += cd.len;
-                    if (cls == 3) farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C);
-                }
-                const unsigned mw = __ballot_sync(0xffffffffu, cls == 1 || cls == 2);
-                const unsigned mm = __ballot_sync(0xffffffffu, cls == 2);
-                const unsigned mf = __ballot_sync(0xffffffffu, cls == 3);
-                const unsigned below = (1u << lane) - 1u;
-                if (cls == 1 || cls == 2) roww[nw + __popc(mw & below)] = make_float4(Uh, L.A_hi, L.a2, L.c1);
-                if (cls == 2) {
-                    int j0, j1;
-                    core_rows(cd, L.A_hi, Uh, j0, j1);
-                    rowc[nm + __popc(mm & below)] =
-                        make_float4(__int_as_float(t | (j0 << 16) | (j1 << 24)), Uh, Ul, wing_tau(L.c1, S_CUT));
-                }
-                nw += __popc(mw);
-                nm += __popc(mm);
-                nf += __popc(mf);
-            }
-            __syncwarp();
-
+            const int NS = P.nslots, CAP = P.list_cap;
             float d[PX], tau[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
                 const int k = j * 32 + lane;
                 d[j] = (k < cd.len) ? __ldg(P.delta_hi + cd.start + k) : 0.0f;
-                tau[j] = 0.0f;
             }
-            // far lines: their summed local expansion, one polynomial per pixel
-            if (nf) {
+            // far lines: sum the slots' partial expansions in slot order (lane n sums coefficient n),
+            // broadcast, one polynomial per pixel
+            {
+                const float *fp = S.farp + (size_t)c * (FF_NC * NS + 1) + (lane < FF_NC ? lane : 0) * NS;
+                float cn = 0.0f;
+                for (int sidx = 0; sidx < NS; ++sidx) cn += fp[sidx];
+                float C[FF_NC];
 #pragma unroll
-                for (int n = 0; n <= FF_DEG; ++n) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) C[n] += __shfl_xor_sync(0xffffffffu, C[n], o);
-                }
+                for (int n = 0; n < FF_NC; ++n) C[n] = __shfl_sync(0xffffffffu, cn, n);
 #pragma unroll
                 for (int j = 0; j < PX; ++j) tau[j] = farfield_eval(C, d[j] * cd.inv_ds);
             }
-            // direct wing form: one LDS.128 per line, 8 evaluations per lane; inside a line core the
+            // near lines, direct wing form: 8 evaluations per lane per line; inside a line core the
             // clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
-            for (int e = 0; e < nw; ++e) {
-                const float4 L = roww[e];
+            int ncore = 0;
+            for (int sidx = 0; sidx < NS; ++sidx) {
+                const int cc = S.cnt[c * NS + sidx];
+                ncore += cc >> 16;
+                const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
+                for (int e = 0; e < (cc & 0xffff); ++e) {
+                    const int2 E = list[e];
+                    const float4 L = *reinterpret_cast<const float4 *>(&S.lp[E.x & 0xffff]);   // A_hi, a2, c1, kappa
+                    const float Uh = __int_as_float(E.y);
 #pragma unroll
-                for (int j = 0; j < PX; ++j) {
-                    const float u = fma32(L.y, d[j], L.x);
-                    const float s = fmaxf(fma32(u, u, L.z), S_CUT);
-                    tau[j] += wing_tau(L.w, s);
+                    for (int j = 0; j < PX; ++j) {
+                        const float u = fma32(L.x, d[j], Uh);
+                        const float s = fmaxf(fma32(u, u, L.y), S_CUT);
+                        tau[j] += wing_tau(L.z, s);
+                    }
                 }
             }
-            // line cores: only the 32-pixel rows a core can reach, accumulated in shared memory (the
-            // row index is dynamic, so the register-resident tau cannot be addressed here)
-            if (nm) {
+            // line cores: only the 32-pixel rows a core can reach.  The row index is dynamic, so the
+            // contributions are accumulated in shared memory -- in the chunk's own (still unused)
+            // slice of the depth buffer -- and added to the register-resident tau afterwards.
+            if (ncore) {
+                float *tcore = S.flux + P.halo + cd.start;
 #pragma unroll
-                for (int j = 0; j < PX; ++j) tcore[j * 32 + lane] = 0.0f;
-                for (int e = 0; e < nm; ++e) {
-                    const float4 E = rowc[e];
-                    const int bits = __float_as_int(E.x);
-                    const int t = bits & 0xffff, j0 = (bits >> 16) & 0xff, j1 = (bits >> 24) & 0xff;
-                    const LineP L = S.lp[t];
-                    if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
-                        // branch-free, two rows in flight: the row loop is latency bound otherwise
+                for (int j = 0; j < PX; ++j)
+                    if (j * 32 + lane < cd.len) tcore[j * 32 + lane] = 0.0f;
+                for (int sidx = 0; sidx < NS; ++sidx) {
+                    const int cc = S.cnt[c * NS + sidx];
+                    if (!(cc >> 16)) continue;
+                    const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
+                    for (int e = 0; e < (cc & 0xffff); ++e) {
+                        const int2 E = list[e];
+                        if (!(E.x & 0x10000)) continue;
+                        const int t = E.x & 0xffff;
+                        const LineP L = S.lp[t];
+                        float Uh, Ul;
+                        split2(S.A64[t] * (cd.rho_s - S.rc64[t]), Uh, Ul);
+                        int j0, j1;
+                        core_rows(cd, L.iA, Uh, j0, j1);
+                        if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
+                            // branch-free, two rows in flight: the row loop is latency bound otherwise
 #pragma unroll 1
-                        for (int j = j0; j <= j1; j += 2) {
-                            const int ka = j * 32 + lane, kb = ka + 32;
-                            const bool va = ka < cd.len, vb = (j < j1) && (kb < cd.len);
-                            const int ia = cd.start + (va ? ka : 0), ib = cd.start + (vb ? kb : 0);
-                            const float dha = __ldg(P.delta_hi + ia), dla = __ldg(P.delta_lo + ia);
-                            const float dhb = __ldg(P.delta_hi + ib), dlb = __ldg(P.delta_lo + ib);
-                            const float ta = tcore[va ? ka : lane], tb = tcore[vb ? kb : lane];
-                            const float ua = fma32(L.A_hi, dha, E.y), ub = fma32(L.A_hi, dhb, E.y);
-                            const bool ca = va && fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
-                            const float uca = ua + fma32(L.A_hi, dla, fma32(L.A_lo, dha, E.z));
-                            const float ucb = ub + fma32(L.A_hi, dlb, fma32(L.A_lo, dhb, E.z));
-                            const float ha = core_h32_lean(L.a, L.a2, uca), hb = core_h32_lean(L.a, L.a2, ucb);
-                            if (ca) tcore[ka] = ta + fma32(L.kappa, ha, -E.w);
-                            if (cb) tcore[kb] = tb + fma32(L.kappa, hb, -E.w);
-                            if (Bt.stats) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
-                        }
-                    } else {
+                            for (int j = j0; j <= j1; j += 2) {
+                                const int ka = j * 32 + lane, kb = ka + 32;
+                                const bool va = ka < cd.len, vb = (j < j1) && (kb < cd.len);
+                                const int ia = cd.start + (va ? ka : 0), ib = cd.start + (vb ? kb : 0);
+                                const float dha = __ldg(P.delta_hi + ia), dla = __ldg(P.delta_lo + ia);
+                                const float dhb = __ldg(P.delta_hi + ib), dlb = __ldg(P.delta_lo + ib);
+                                const float ta = tcore[va ? ka : 0], tb = tcore[vb ? kb : 0];
+                                const float ua = fma32(L.A_hi, dha, Uh), ub = fma32(L.A_hi, dhb, Uh);
+                                const bool ca = va && fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
+                                const float uca = ua + fma32(L.A_hi, dla, fma32(L.A_lo, dha, Ul));
+                                const float ucb = ub + fma32(L.A_hi, dlb, fma32(L.A_lo, dhb, Ul));
+                                const float ha = core_h32_lean(L.a, L.a2, uca), hb = core_h32_lean(L.a, L.a2, ucb);
+                                if (ca) tcore[ka] = ta + fma32(L.kappa, ha, -L.c1w);
+                                if (cb) tcore[kb] = tb + fma32(L.kappa, hb, -L.c1w);
+                                if (Bt.stats) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
+                            }
+                        } else {
 #pragma unroll 1
-                        for (int j = j0; j <= j1; ++j) {
-                            const int k = j * 32 + lane;
-                            if (k < cd.len) {
-                                const float dh = __ldg(P.delta_hi + cd.start + k);
-                                const float u = fma32(L.A_hi, dh, E.y);
-                                const float s = fma32(u, u, L.a2);
-                                if (s < S_CUT) {
-                                    const float dl = __ldg(P.delta_lo + cd.start + k);
-                                    float uh, ul;
-                                    core_u2(L.A_hi, L.A_lo, dh, dl, E.y, E.z, uh, ul);
-                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -E.w);
-                                    if (Bt.stats) st_core += 1;
+                            for (int j = j0; j <= j1; ++j) {
+                                const int k = j * 32 + lane;
+                                if (k < cd.len) {
+                                    const float dh = __ldg(P.delta_hi + cd.start + k);
+                                    const float u = fma32(L.A_hi, dh, Uh);
+                                    const float s = fma32(u, u, L.a2);
+                                    if (s < S_CUT) {
+                                        const float dl = __ldg(P.delta_lo + cd.start + k);
+                                        float uh, ul;
+                                        core_u2(L.A_hi, L.A_lo, dh, dl, Uh, Ul, uh, ul);
+                                        tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -L.c1w);
+                                        if (Bt.stats) st_core += 1;
+                                    }
                                 }
                             }
                         }
                     }
                 }
 #pragma unroll
-                for (int j = 0; j < PX; ++j) tau[j] += tcore[j * 32 + lane];
-            }
-            if (Bt.stats && lane == 0) {
-                st_wing += (unsigned long long)(nw - nm) * cd.len;
-                st_mixed += (unsigned long long)nm * cd.len;
-                st_total += (unsigned long long)h.nact * cd.len;
-                st_far += (unsigned long long)nf * cd.len;
-                st_farchunks += nf ? 1 : 0;
+                for (int j = 0; j < PX; ++j)
+                    if (j * 32 + lane < cd.len) tau[j] += tcore[j * 32 + lane];
             }
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
@@ -469,7 +498,6 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         st_cull = (unsigned long long)warp_sum((double)st_cull);
         st_total = (unsigned long long)warp_sum((double)st_total);
         st_far = (unsigned long long)warp_sum((double)st_far);
-        st_farchunks = (unsigned long long)warp_sum((double)st_farchunks);
         if (lane == 0) {
             atomicAdd(Bt.stats + 0, st_total);
             atomicAdd(Bt.stats + 1, st_wing);
@@ -477,7 +505,6 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             atomicAdd(Bt.stats + 3, st_core);
             atomicAdd(Bt.stats + 4, st_cull);
             atomicAdd(Bt.stats + 5, st_far);
-            atomicAdd(Bt.stats + 6, st_farchunks);
         }
     }
 }
@@ -627,20 +654,8 @@ __global__ void mcalf_ffma_peak_kernel(float *out, int iters) {
 namespace mcalf {
 
 size_t fast_smem_bytes(const DevProblem &P, int nwarps) {
-    size_t o = 0;
-    auto take = [&](size_t bytes) { o += (bytes + 15) & ~(size_t)15; };
-    take(sizeof(double) * P.ndim_pad);
-    take(sizeof(double) * P.Lmax);
-    take(sizeof(double) * P.Lmax);
-    take(sizeof(LineP) * P.Lmax);
-    take(sizeof(float4) * P.Lmax * nwarps);
-    take(sizeof(float4) * P.Lmax * nwarps);
-    take(sizeof(float) * PX * 32 * nwarps);
-    take(sizeof(float) * (2 * P.nmax4 + 8));
-    take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
-    take(sizeof(double) * 64);
-    take(sizeof(int) * 8);
-    return o;
+    (void)nwarps;
+    return carve(nullptr, P).bytes;
 }
 
 size_t fp64_smem_bytes(const DevProblem &P) {

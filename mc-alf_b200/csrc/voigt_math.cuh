@@ -253,7 +253,7 @@ struct Line64 {
 // 32 bytes: what the mixed (core-containing) path reads per line
 struct LineP {
     float A_hi, a2, c1, kappa;   // c1 = kappa*a/sqrt(pi): the wing amplitude
-    float A_lo, a, pad0, pad1;
+    float A_lo, a, c1w, iA;      // c1w = wing value at s = S_CUT (what the clamped direct form adds inside a core); iA = 1/A
 };
 
 MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, double f, double gamma,
@@ -285,7 +285,8 @@ MCALF_HD LineP line_pack(const Line64 &L) {
     o.a2 = (float)(L.a * L.a);
     o.c1 = (float)(L.kappa * L.a / SQRTPI_D);
     o.kappa = (float)L.kappa;
-    o.pad0 = o.pad1 = 0.0f;
+    o.c1w = 0.0f;
+    o.iA = (float)(1.0 / L.A);
     return o;
 }
 
@@ -362,6 +363,12 @@ MCALF_HD float wing_tau(float c1, float s) {
     p = fma32(p, q, w[1]);
     p = fma32(p, q, w[0]);
     return (c1 * q) * p;
+}
+
+MCALF_HD LineP line_pack_full(const Line64 &L) {
+    LineP o = line_pack(L);
+    o.c1w = wing_tau(o.c1, S_CUT);
+    return o;
 }
 
 // two-float u = A*delta + U for the line core

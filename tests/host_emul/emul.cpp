@@ -57,7 +57,7 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
             for (int t = 0; t < nlines; ++t) {
                 const double *l = lines + 6 * t;
                 const Line64 L64 = line_setup64(l[0], l[1], l[2], l[3], l[4], l[5], lam_ref);
-                const LineP L = line_pack(L64);
+                const LineP L = line_pack_full(L64);
                 const double U = L64.A * (cd.rho_s - L64.rc);
                 float Uh, Ul;
                 split2(U, Uh, Ul);
