@@ -344,7 +344,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
 
     // per-pixel tables
     std::vector<double> wave(p->wave, p->wave + npix), obj(npix), w(npix), obj_raw(p->flux, p->flux + npix), isig(npix);
-    std::vector<float4> pix(npix);
+    std::vector<float> obj_hi(P.npix4, 0.0f), obj_lo(P.npix4, 0.0f), w32(P.npix4, 0.0f);
     double csum = 0.0;
     P.chi2_add = 0.0;
     for (int i = 0; i < npix; ++i) {
@@ -365,8 +365,9 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
             // chi2 (:246) has no -log(w) term: a zero-error pixel contributes inf*(resid^2) = +inf there
             if (er == 0.0 && !(f != f)) P.chi2_add = INFINITY;
         }
-        const float oh = (float)obj[i];
-        pix[i] = make_float4(oh, (float)(obj[i] - (double)oh), (float)w[i], 0.0f);
+        obj_hi[i] = (float)obj[i];
+        obj_lo[i] = (float)(obj[i] - (double)obj_hi[i]);
+        w32[i] = (float)w[i];
     }
     P.logC = -0.5 * csum;
 
@@ -391,10 +392,14 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     std::vector<double> blo(p->bounds_lo, p->bounds_lo + ndim), bhi(p->bounds_hi, p->bounds_hi + ndim);
 
     int rc;
+#define UPF4(vec, field) { const float *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) { mcalf_destroy(c); return rc; } P.field = reinterpret_cast<const float4 *>(tmp_); }
 #define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) { mcalf_destroy(c); return rc; }
-    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(pix, pix) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
+    std::vector<float2> d2(npix);
+    for (int i = 0; i < npix; ++i) d2[i] = make_float2(dhi[i], dlo[i]);
+    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
     UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)
 #undef UP
+#undef UPF4
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) { mcalf_destroy(c); return fail(MCALF_E_CUDA, "stats buffer: %s", cudaGetErrorString(e)); }

@@ -22,7 +22,9 @@ struct DevProblem {
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
     const float *delta_hi, *delta_lo;   // [npix] rho_i - rho_s(chunk) as a two-float
-    const float4 *pix;                  // [npix] {obj_hi, obj_lo, w, 0}; obj = w = 0 on dropped pixels
+    const float2 *delta2;               // [npix] the same, interleaved {hi, lo} (line-core pass)
+    const float4 *obj_hi4, *obj_lo4, *w4; // [npix4/4] flux as a two-float and weight 1/err^2, four pixels per element;
+                                        // obj = w = 0 on dropped pixels and on the padding
     const ChunkDesc *chunks;            // [nchunks]
     const double *wave, *obj, *w;       // [npix] fp64 copies for the check kernel (obj = w = 0 on dropped pixels)
     const double *obj_raw, *isig;       // [npix] untouched flux and 1/err for the Asymmlike counts

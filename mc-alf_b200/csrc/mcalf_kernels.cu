@@ -125,22 +125,18 @@ __device__ __forceinline__ int build_taps(const DevProblem &P, double specres, f
 // ---------------------------------------------------------------------------------------------
 constexpr int PX = 8;            // pixels per lane per chunk (chunk = 32 lanes x 8 = 256 pixels)
 
-// Rows (32 consecutive pixels) of chunk `cd` that the core |u| < U_CORE_MARGIN of a line can reach, from
-// the chunk's linear pixel <-> delta model; kslack (host computed) bounds the model's error in pixels.
-__device__ __forceinline__ void core_rows(const ChunkDesc &cd, float iA, float U_hi, int &j0, int &j1) {
+// Pixels [k_lo, k_hi] of chunk `cd` that the core |u| < U_CORE_MARGIN of a line can reach (a superset:
+// the loop still tests every pixel), from the chunk's linear pixel <-> delta model; kslack (host computed)
+// bounds the model's error in pixels.  Empty when k_lo > k_hi.
+__device__ __forceinline__ void core_range(const ChunkDesc &cd, float iA, float U_hi, int &k_lo, int &k_hi) {
     const float ka = ((-U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
     const float kb = ((U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
     float lo = fminf(ka, kb) - (float)cd.kslack, hi = fmaxf(ka, kb) + (float)cd.kslack;
+    if (!(lo == lo) || !(hi == hi)) { lo = 0.0f; hi = (float)CHUNK_PIXELS; }      // NaN: every pixel is a candidate
     lo = fmaxf(lo, 0.0f);
     hi = fminf(hi, (float)(cd.len - 1));
-    if (!(lo <= hi)) {                 // empty (or NaN): no row
-        j0 = 1;
-        j1 = 0;
-        if (!(lo == lo) || !(hi == hi)) { j0 = 0; j1 = PX - 1; }
-        return;
-    }
-    j0 = (int)lo >> 5;
-    j1 = (int)hi >> 5;
+    k_lo = (int)lo;
+    k_hi = (lo <= hi) ? (int)hi : -1;
 }
 
 constexpr int FF_NC = FF_DEG + 1;
@@ -349,22 +345,23 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         const LineP L = S.lp[t];
                         float Uh, Ul;
                         split2(S.A64[t] * (cd.rho_s - S.rc64[t]), Uh, Ul);
-                        int j0, j1;
-                        core_rows(cd, L.iA, Uh, j0, j1);
+                        int k_lo, k_hi;
+                        core_range(cd, L.iA, Uh, k_lo, k_hi);
+                        const float2 *dd = P.delta2 + cd.start;
                         if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
-                            // branch-free, two rows in flight: the row loop is latency bound otherwise
+                            // branch-free, 64 consecutive pixels per trip (two per lane in flight): the
+                            // loop is latency bound otherwise
 #pragma unroll 1
-                            for (int j = j0; j <= j1; j += 2) {
-                                const int ka = j * 32 + lane, kb = ka + 32;
-                                const bool va = ka < cd.len, vb = (j < j1) && (kb < cd.len);
-                                const int ia = cd.start + (va ? ka : 0), ib = cd.start + (vb ? kb : 0);
-                                const float dha = __ldg(P.delta_hi + ia), dla = __ldg(P.delta_lo + ia);
-                                const float dhb = __ldg(P.delta_hi + ib), dlb = __ldg(P.delta_lo + ib);
-                                const float ta = tcore[va ? ka : 0], tb = tcore[vb ? kb : 0];
-                                const float ua = fma32(L.A_hi, dha, Uh), ub = fma32(L.A_hi, dhb, Uh);
-                                const bool ca = va && fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
-                                const float uca = ua + fma32(L.A_hi, dla, fma32(L.A_lo, dha, Ul));
-                                const float ucb = ub + fma32(L.A_hi, dlb, fma32(L.A_lo, dhb, Ul));
+                            for (int ka = k_lo + lane; ka <= k_hi; ka += 64) {
+                                const int kb = ka + 32;
+                                const bool vb = kb <= k_hi;
+                                const int kbs = vb ? kb : ka;
+                                const float2 da = __ldg(dd + ka), db = __ldg(dd + kbs);
+                                const float ta = tcore[ka], tb = tcore[kbs];
+                                const float ua = fma32(L.A_hi, da.x, Uh), ub = fma32(L.A_hi, db.x, Uh);
+                                const bool ca = fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
+                                const float uca = ua + fma32(L.A_hi, da.y, fma32(L.A_lo, da.x, Ul));
+                                const float ucb = ub + fma32(L.A_hi, db.y, fma32(L.A_lo, db.x, Ul));
                                 const float ha = core_h32_lean(L.a, L.a2, uca), hb = core_h32_lean(L.a, L.a2, ucb);
                                 if (ca) tcore[ka] = ta + fma32(L.kappa, ha, -L.c1w);
                                 if (cb) tcore[kb] = tb + fma32(L.kappa, hb, -L.c1w);
@@ -372,19 +369,15 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                             }
                         } else {
 #pragma unroll 1
-                            for (int j = j0; j <= j1; ++j) {
-                                const int k = j * 32 + lane;
-                                if (k < cd.len) {
-                                    const float dh = __ldg(P.delta_hi + cd.start + k);
-                                    const float u = fma32(L.A_hi, dh, Uh);
-                                    const float s = fma32(u, u, L.a2);
-                                    if (s < S_CUT) {
-                                        const float dl = __ldg(P.delta_lo + cd.start + k);
-                                        float uh, ul;
-                                        core_u2(L.A_hi, L.A_lo, dh, dl, Uh, Ul, uh, ul);
-                                        tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -L.c1w);
-                                        if (Bt.stats) st_core += 1;
-                                    }
+                            for (int k = k_lo + lane; k <= k_hi; k += 32) {
+                                const float2 dk = __ldg(dd + k);
+                                const float u = fma32(L.A_hi, dk.x, Uh);
+                                const float s = fma32(u, u, L.a2);
+                                if (s < S_CUT) {
+                                    float uh, ul;
+                                    core_u2(L.A_hi, L.A_lo, dk.x, dk.y, Uh, Ul, uh, ul);
+                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -L.c1w);
+                                    if (Bt.stats) st_core += 1;
                                 }
                             }
                         }
@@ -423,6 +416,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         int cnt5 = 0, cnt4 = 0;
         const int ngroups = P.npix4 >> 2;
         const int nb = (n4 >> 1) + 1;
+        const bool extras = Bt.flux_out != nullptr || P.asymmlike;
         for (int g = tid; g < ngroups; g += nthreads) {
             const int o0 = g << 2;
             const float4 *xin = reinterpret_cast<const float4 *>(S.flux + (P.halo + o0 - n4));
@@ -438,30 +432,36 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 o_0 = fma32(gg.w, xl.w, o_0); o_1 = fma32(gg.w, xh.x, o_1); o_2 = fma32(gg.w, xh.y, o_2); o_3 = fma32(gg.w, xh.z, o_3);
                 xl = xh;
             }
-            const float out[4] = {o_0, o_1, o_2, o_3};
-            float part = 0.f;
+            // shared memory holds the absorption DEPTH 1 - exp(-tau); with unit-sum taps the convolved
+            // model is cont * (1 - conv(depth)), so every rounding error scales with the depth, not with
+            // the continuum (a coherent 1e-7 bias of the continuum level would move chi-square by
+            // 2 w sum(resid) 1e-7 -- not small for one-signed residuals).  The pixel tables are padded
+            // to a multiple of four with w = 0, so no pixel needs a bounds test here.
+            const float4 oh = __ldg(P.obj_hi4 + g), ol = __ldg(P.obj_lo4 + g), ww = __ldg(P.w4 + g);
+            const float r0 = fma32(c_hi, o_0, (oh.x - c_hi) + (ol.x - c_lo)) + c_lo * o_0;
+            const float r1 = fma32(c_hi, o_1, (oh.y - c_hi) + (ol.y - c_lo)) + c_lo * o_1;
+            const float r2 = fma32(c_hi, o_2, (oh.z - c_hi) + (ol.z - c_lo)) + c_lo * o_2;
+            const float r3 = fma32(c_hi, o_3, (oh.w - c_hi) + (ol.w - c_lo)) + c_lo * o_3;
+            float part = (ww.x * r0) * r0;
+            part = fma32(ww.y * r1, r1, part);
+            part = fma32(ww.z * r2, r2, part);
+            part = fma32(ww.w * r3, r3, part);
+            if (extras) {
+                const float out[4] = {o_0, o_1, o_2, o_3};
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const int o = o0 + r;
-                if (o < P.npix) {
-                    // shared memory holds the absorption DEPTH 1 - exp(-tau); with unit-sum taps the
-                    // convolved model is cont * (1 - conv(depth)), so every rounding error scales with the
-                    // depth, not with the continuum (a coherent 1e-7 bias of the continuum level would move
-                    // chi-square by 2 w sum(resid) 1e-7 -- not small for one-signed residuals)
-                    const float4 px = __ldg(P.pix + o);            // {obj_hi, obj_lo, w, 0}
-                    const float dep = out[r];
-                    const float base = (px.x - c_hi) + (px.y - c_lo);
-                    const float res = fma32(c_hi, dep, base) + c_lo * dep;
-                    part = fma32(px.z * res, res, part);
-                    if (Bt.flux_out) {
-                        const double md = h.cont - h.cont * (double)dep;
-                        if (flags & MCALF_F_FLUX_F64) ((double *)Bt.flux_out)[b * (long long)P.npix + o] = md;
-                        else ((float *)Bt.flux_out)[b * (long long)P.npix + o] = (float)md;
-                    }
-                    if (P.asymmlike) {
-                        const double rs = (P.obj_raw[o] - (h.cont - h.cont * (double)dep)) * P.isig[o];
-                        cnt5 += rs > 5.0;
-                        cnt4 += rs > 4.0;
+                for (int r = 0; r < 4; ++r) {
+                    const int o = o0 + r;
+                    if (o < P.npix) {
+                        const double md = h.cont - h.cont * (double)out[r];
+                        if (Bt.flux_out) {
+                            if (flags & MCALF_F_FLUX_F64) ((double *)Bt.flux_out)[b * (long long)P.npix + o] = md;
+                            else ((float *)Bt.flux_out)[b * (long long)P.npix + o] = (float)md;
+                        }
+                        if (P.asymmlike) {
+                            const double rs = (P.obj_raw[o] - md) * P.isig[o];
+                            cnt5 += rs > 5.0;
+                            cnt4 += rs > 4.0;
+                        }
                     }
                 }
             }
