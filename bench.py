@@ -41,11 +41,15 @@ UNIT = "logL/s"
 WORKLOAD = "cfg4: 8192 px x 20 comps x 2 lines (CIV doublet), free specres+continuum, ndim 63"
 
 # executed FP32 flops per unit of each path of mcalf_fast_kernel (FMA = 2, add/mul/min/max/rint = 1,
-# MUFU.RCP = 1); derivation in DESIGN.md section 5
-FLOP_WING = 16
-FLOP_MIXED = 17
-FLOP_CORE_EXTRA = 70
-FLOP_PIXEL = 33          # depth32 (23) + residual / chi-square (10); the stencil adds 2 per padded tap
+# MUFU = 1); derivation in DESIGN.md section 5
+FLOP_PAIR_CLASS = 18     # chunk_class per (line, chunk) pair
+FLOP_PAIR_FAR = 58       # farfield_accumulate per far pair
+FLOP_NEAR_EVAL = 17      # direct wing form per (line, pixel) of a near (wing or mixed) pair
+FLOP_CORE_LEAN = 38      # extra per line-core pixel, weak line
+FLOP_CORE_PRECISE = 75   # extra per line-core pixel, strong line (two-float coordinate, polynomial exp)
+FLOP_CHUNK = 48          # summing the slots' far-field partials, per (sample, chunk)
+FLOP_PIXEL = 44          # far-field polynomial (11) + depth32 (23) + residual / chi-square (10); stencil: 2 per padded tap
+CHUNK = 256
 # SURVEY 8d canonical counts (Weideman-32 core, 3-term asymptotic wing)
 CANON_EVAL = 5.0
 CANON_CORE, CANON_WING = 242.0, 36.0
@@ -281,7 +285,11 @@ def run_ours(args):
         n = np.where(P[:, 0] > g.velstep, np.ceil(3.0348 * sig), 0)
         taps_padded = 2 * (4 * np.ceil(n / 4)) + 4
         npix = g.obj_wl.size
-        flop = (FLOP_WING * st["evals_wing"] + FLOP_MIXED * st["evals_mixed"] + FLOP_CORE_EXTRA * st["evals_core"]
+        near = st["evals_wing"] + st["evals_mixed"]
+        pairs = st["evals_total"] / CHUNK
+        flop = (FLOP_PAIR_CLASS * pairs + FLOP_PAIR_FAR * st["evals_far"] / CHUNK + FLOP_NEAR_EVAL * near
+                + FLOP_CORE_LEAN * (st["evals_core"] - st["evals_core_precise"])
+                + FLOP_CORE_PRECISE * st["evals_core_precise"] + FLOP_CHUNK * geo["nchunks"] * B
                 + npix * (FLOP_PIXEL * B + 2.0 * taps_padded.sum()))
         f_core_canon = 2.0 * math.sqrt(111.0) * np.mean(P[:, 5::3][:, :20]) / g.velstep / npix   # SURVEY 8d estimate
         canon = (st["evals_total"] * (CANON_EVAL + f_core_canon * CANON_CORE + (1 - f_core_canon) * CANON_WING)
@@ -302,6 +310,7 @@ def run_ours(args):
             "kernel": "mcalf_fast_kernel", "kernel_ms": kernel_ms, "flop_per_logL": flop / B,
             "evals_per_logL": st["evals_total"] / B, "frac_wing": st["evals_wing"] / st["evals_total"],
             "frac_mixed": st["evals_mixed"] / st["evals_total"], "frac_core": st["evals_core"] / st["evals_total"],
+            "frac_far": st["evals_far"] / st["evals_total"],
             "canonical_flop_per_logL": canon / B, "canonical_tflops": canon / (kernel_ms * 1e-3) / 1e12,
             "canonical_frac_of_nominal": canon / (kernel_ms * 1e-3) / 1e12 / peak_nominal,
             "hbm_bytes_per_logL": g.ndim * 8 + 8,

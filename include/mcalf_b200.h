@@ -84,7 +84,7 @@ typedef struct mcalf_stats {
     uint64_t evals_core;       /* ... of the mixed ones that took the line-core branch                  */
     uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound                     */
     uint64_t evals_far;        /* ... in pairs folded into the chunk's far-field polynomial             */
-    uint64_t far_chunks;       /* (sample, chunk) pairs that evaluated a far-field polynomial           */
+    uint64_t evals_core_precise; /* ... of the core ones that took the two-float form (kappa > 8)          */
     double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events)            */
 } mcalf_stats_t;
 

@@ -39,7 +39,7 @@ class Stats(ctypes.Structure):
     """mcalf_stats_t"""
     _fields_ = [(n, ctypes.c_uint64) for n in
                 ("kernel_launches", "samples", "samples_fp64", "evals_total", "evals_wing", "evals_mixed",
-                 "evals_core", "evals_culled", "evals_far", "far_chunks")] + [("last_kernel_ms", ctypes.c_double)]
+                 "evals_core", "evals_culled", "evals_far", "evals_core_precise")] + [("last_kernel_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

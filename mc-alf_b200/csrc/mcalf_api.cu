@@ -375,12 +375,13 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     std::vector<float> dhi, dlo;
     build_chunks(wave.data(), npix, P.lam_ref, chunks, dhi, dlo);
     P.nchunks = (int)chunks.size();
-    {   // pass-A geometry: lane groups of cslot_w chunks, 8 virtual warps
+    {   // pass-A geometry: lane groups of cslot_w chunks
         int w = 1, lw = 0;
         while (w < 32 && w < P.nchunks) { w <<= 1; ++lw; }
         P.cslot_w = w;
         P.cslot_lw = lw;
-        P.nslots = 8 * (32 / w);
+        P.vwarps = std::max(1, 8 / (32 / w));      // about eight slots whatever the chunk count
+        P.nslots = P.vwarps * (32 / w);
         P.list_cap = (P.Lmax + P.nslots - 1) / P.nslots;
     }
 
@@ -533,7 +534,7 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     out->evals_core = h[3];
     out->evals_culled = h[4];
     out->evals_far = h[5];
-    out->far_chunks = h[6];
+    out->evals_core_precise = h[6];
     if (c->last_slot >= 0) {
         float ms = 0.f;
         Slot &s = c->slot[c->last_slot];

@@ -16,7 +16,7 @@ struct DevProblem {
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
     int Lmax, list_cap;                 // list_cap: entries per (chunk, slot) sub-list
-    int cslot_w, cslot_lw, nslots, pad_; // lanes per chunk group (power of two), its log2, slots = 8 * 32 / cslot_w
+    int cslot_w, cslot_lw, nslots, vwarps; // lanes per chunk group (power of two), its log2, slots = vwarps * 32 / cslot_w
     float eps_cull, eps_far;
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;
@@ -41,7 +41,7 @@ struct BatchArgs {
     unsigned int *work_counter;         // zeroed before the launch
     unsigned int *fallback_count;       // zeroed before the launch
     int *fallback_list;                 // [B]
-    unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far} evaluations, far chunks
+    unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far, core-precise} evaluations
 };
 
 size_t fast_smem_bytes(const DevProblem &P, int nwarps);

@@ -140,8 +140,8 @@ __device__ __forceinline__ void core_range(const ChunkDesc &cd, float iA, float 
 }
 
 constexpr int FF_NC = FF_DEG + 1;
-constexpr int VWARPS = 8;        // virtual warps of the classification pass: fixes its summation and list
-                                 // order whatever the CTA size, so results do not depend on the launch geometry
+// The classification pass runs on P.vwarps "virtual warps" (a problem constant, not the CTA size): its
+// summation and list order, hence every result bit, is independent of the launch geometry.
 
 struct FastSmem {
     double *theta;     // [ndim_pad]
@@ -186,7 +186,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     const uint32_t flags = Bt.flags;
 
     // per-thread statistics (only summed when Bt.stats != nullptr)
-    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0;
+    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0;
 
     for (;;) {
         // ---- next sample (dynamic: the active-component count varies per sample) ----
@@ -232,12 +232,12 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 
         // ---- pass A: classify every (line, chunk) pair, lane = chunk ----
         // Far pairs fold into per-(chunk, slot) partial expansions, near pairs are listed per
-        // (chunk, slot).  A slot is one lane group of one of VWARPS virtual warps and owns the lines
+        // (chunk, slot).  A slot is one lane group of one of P.vwarps virtual warps and owns the lines
         // slot, slot + nslots, ...; sums and lists are later read in slot order.
         {
             const int W = P.cslot_w, LW = P.cslot_lw, SUB = 32 >> LW, NS = P.nslots, CAP = P.list_cap;
             const int fstride = FF_NC * NS + 1;
-            for (int vw = warp; vw < VWARPS; vw += nwarps) {
+            for (int vw = warp; vw < P.vwarps; vw += nwarps) {
                 const int slot = vw * SUB + (lane >> LW);
                 for (int cg = 0; cg < P.nchunks; cg += W) {
                     const int c = cg + (lane & (W - 1));
@@ -377,7 +377,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                                     float uh, ul;
                                     core_u2(L.A_hi, L.A_lo, dk.x, dk.y, Uh, Ul, uh, ul);
                                     tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -L.c1w);
-                                    if (Bt.stats) st_core += 1;
+                                    if (Bt.stats) { st_core += 1; st_corep += 1; }
                                 }
                             }
                         }
@@ -498,6 +498,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         st_cull = (unsigned long long)warp_sum((double)st_cull);
         st_total = (unsigned long long)warp_sum((double)st_total);
         st_far = (unsigned long long)warp_sum((double)st_far);
+        st_corep = (unsigned long long)warp_sum((double)st_corep);
         if (lane == 0) {
             atomicAdd(Bt.stats + 0, st_total);
             atomicAdd(Bt.stats + 1, st_wing);
@@ -505,6 +506,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             atomicAdd(Bt.stats + 3, st_core);
             atomicAdd(Bt.stats + 4, st_cull);
             atomicAdd(Bt.stats + 5, st_far);
+            atomicAdd(Bt.stats + 6, st_corep);
         }
     }
 }

@@ -1,0 +1,66 @@
+"""CPU: solver adapters against fakes (the samplers themselves are not installed)."""
+import numpy as np
+
+from mcalf_b200.solvers import BatchPool
+
+
+class FakeFitter:
+    """Stands in for als_fitter: same method names, counts batched launches."""
+    ndim = 3
+
+    def __init__(self):
+        self.batches = []
+
+    def lnlhood_batch(self, P):
+        self.batches.append(len(P))
+        return -np.sum(np.asarray(P) ** 2, axis=1)
+
+    def prior_transform_batch(self, U):
+        self.batches.append(len(U))
+        return np.asarray(U) * 2.0
+
+    def lnlhood_worker(self, p):
+        return float(self.lnlhood_batch(np.asarray(p)[None, :])[0])
+
+    def lnlhood_dy(self, p):
+        return self.lnlhood_worker(p)
+
+    def lnlhood_pc(self, p):
+        return self.lnlhood_worker(p), []
+
+    def _scale_cube_pc(self, u):
+        return np.asarray(u) * 2.0
+
+
+class Wrapper:           # how dynesty wraps user callables
+    def __init__(self, func):
+        self.func = func
+
+    def __call__(self, x):
+        return self.func(x)
+
+
+def test_pool_batches_likelihood_calls():
+    f = FakeFitter()
+    pool = BatchPool(f)
+    pts = [np.array([1.0, 2.0, 3.0]) * k for k in range(5)]
+    out = pool.map(f.lnlhood_dy, pts)
+    assert f.batches == [5] and pool.launches == 1
+    assert np.allclose(out, [-14.0 * k * k for k in range(5)])
+    out = pool.map(Wrapper(f.lnlhood_dy), pts)          # wrapped callable is recognised too
+    assert f.batches == [5, 5]
+    out = pool.map(f.lnlhood_pc, pts)
+    assert out[2] == (-56.0, []) and f.batches == [5, 5, 5]
+    out = pool.map(f._scale_cube_pc, pts)
+    assert np.array_equal(out[1], pts[1] * 2) and f.batches[-1] == 5
+    assert pool.map(f.lnlhood_dy, []) == []
+
+
+def test_pool_falls_back_for_foreign_functions():
+    f = FakeFitter()
+    pool = BatchPool(f)
+    assert pool.map(lambda x: x + 1, [1, 2, 3]) == [2, 3, 4]
+    assert f.batches == []
+    other = FakeFitter()
+    pool.map(other.lnlhood_dy, [np.zeros(3)])            # another fitter's method: not batched through ours
+    assert f.batches == [] and other.batches == [1]
