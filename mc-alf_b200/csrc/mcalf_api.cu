@@ -395,7 +395,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     int rc;
 #define UPF4(vec, field) { const float *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) { mcalf_destroy(c); return rc; } P.field = reinterpret_cast<const float4 *>(tmp_); }
 #define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) { mcalf_destroy(c); return rc; }
-    std::vector<float2> d2(npix);
+    std::vector<float2> d2(npix + 64, make_float2(0.f, 0.f));      // padded: the core pass reads 32 ahead unguarded
     for (int i = 0; i < npix; ++i) d2[i] = make_float2(dhi[i], dlo[i]);
     UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
     UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)

@@ -151,6 +151,7 @@ struct FastSmem {
     int2 *wl;          // [nchunks][nslots][list_cap]  near lines of a chunk: {line | core << 16, U_hi bits}
     float *farp;       // [nchunks][FF_NC * nslots + 1] partial far-field coefficients, [n][slot] within a chunk
     int *cnt;          // [nchunks][nslots]            entries in each sub-list | core entries << 16
+    G1Row *g1;         // [MCALF_G1_N] Taylor rows of H1 (line-core form)
     float *taps;       // [2*nmax4 + 8]
     float *flux;       // [halo + npix4 + halo + 8]
     double *red;       // [64]
@@ -169,6 +170,7 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     s.wl = (int2 *)take(sizeof(int2) * (size_t)P.nchunks * P.nslots * P.list_cap);
     s.farp = (float *)take(sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
     s.cnt = (int *)take(sizeof(int) * (size_t)P.nchunks * P.nslots);
+    s.g1 = (G1Row *)take(sizeof(G1Row) * MCALF_G1_N);
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
@@ -177,6 +179,7 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     return s;
 }
 
+template <bool STATS>
 __global__ void __launch_bounds__(1024, 1)
 mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ BatchArgs Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -185,6 +188,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     FastSmem S = carve(smem_raw, P);
     const uint32_t flags = Bt.flags;
 
+    for (int i = tid; i < MCALF_G1_N; i += nthreads) S.g1[i] = g1_tab_dev[i];
     // per-thread statistics (only summed when Bt.stats != nullptr)
     unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0;
 
@@ -259,7 +263,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                             list[nw++] = make_int2(t | (cls == 2 ? 0x10000 : 0), __float_as_int(Uh));
                             nc += cls == 2;
                         }
-                        if (Bt.stats) {
+                        if (STATS) {
                             const int len = cact ? P.chunks[c].len : 0;
                             st_total += len;
                             st_cull += cls == 0 ? len : 0;
@@ -351,21 +355,23 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
                             // branch-free, 64 consecutive pixels per trip (two per lane in flight): the
                             // loop is latency bound otherwise
+                            // (the delta table is padded by 64 entries, so the second load needs no bounds test)
+                            const float2 *pa = dd + k_lo + lane;
+                            float *ta_p = tcore + k_lo + lane;
 #pragma unroll 1
-                            for (int ka = k_lo + lane; ka <= k_hi; ka += 64) {
-                                const int kb = ka + 32;
-                                const bool vb = kb <= k_hi;
-                                const int kbs = vb ? kb : ka;
-                                const float2 da = __ldg(dd + ka), db = __ldg(dd + kbs);
-                                const float ta = tcore[ka], tb = tcore[kbs];
+                            for (int ka = k_lo + lane; ka <= k_hi; ka += 64, pa += 64, ta_p += 64) {
+                                const bool vb = ka + 32 <= k_hi;
+                                const float2 da = __ldg(pa), db = __ldg(pa + 32);
+                                const float ta = ta_p[0];
+                                const float tb = vb ? ta_p[32] : 0.0f;
                                 const float ua = fma32(L.A_hi, da.x, Uh), ub = fma32(L.A_hi, db.x, Uh);
                                 const bool ca = fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
                                 const float uca = ua + fma32(L.A_hi, da.y, fma32(L.A_lo, da.x, Ul));
                                 const float ucb = ub + fma32(L.A_hi, db.y, fma32(L.A_lo, db.x, Ul));
-                                const float ha = core_h32_lean(L.a, L.a2, uca), hb = core_h32_lean(L.a, L.a2, ucb);
-                                if (ca) tcore[ka] = ta + fma32(L.kappa, ha, -L.c1w);
-                                if (cb) tcore[kb] = tb + fma32(L.kappa, hb, -L.c1w);
-                                if (Bt.stats) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
+                                const float ha = core_h32_lean(L.a, L.a2, uca, S.g1), hb = core_h32_lean(L.a, L.a2, ucb, S.g1);
+                                if (ca) ta_p[0] = ta + fma32(L.kappa, ha, -L.c1w);
+                                if (cb) ta_p[32] = tb + fma32(L.kappa, hb, -L.c1w);
+                                if (STATS) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
                             }
                         } else {
 #pragma unroll 1
@@ -376,8 +382,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                                 if (s < S_CUT) {
                                     float uh, ul;
                                     core_u2(L.A_hi, L.A_lo, dk.x, dk.y, Uh, Ul, uh, ul);
-                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul), -L.c1w);
-                                    if (Bt.stats) { st_core += 1; st_corep += 1; }
+                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul, S.g1), -L.c1w);
+                                    if (STATS) { st_core += 1; st_corep += 1; }
                                 }
                             }
                         }
@@ -491,7 +497,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         }
     }
 
-    if (Bt.stats) {
+    if (STATS) {
         st_wing = (unsigned long long)warp_sum((double)st_wing);   // exact below 2^53
         st_mixed = (unsigned long long)warp_sum((double)st_mixed);
         st_core = (unsigned long long)warp_sum((double)st_core);
@@ -665,17 +671,20 @@ size_t fp64_smem_bytes(const DevProblem &P) {
 }
 
 cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mcalf_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    cudaError_t e = cudaFuncSetAttribute(mcalf_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mcalf_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(mcalf_fp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp64_bytes);
 }
 
 cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false>, threads, smem);
 }
 
 cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st) {
-    mcalf_fast_kernel<<<grid, threads, smem, st>>>(P, Bt);
+    if (Bt.stats) mcalf_fast_kernel<true><<<grid, threads, smem, st>>>(P, Bt);
+    else mcalf_fast_kernel<false><<<grid, threads, smem, st>>>(P, Bt);
     return cudaGetLastError();
 }
 

@@ -37,7 +37,7 @@ constexpr double SQRTPI_D = 1.77245385090551602730;
 constexpr float S_CUT = MCALF_S_CUT;
 constexpr double A_MAX_FAST = 0.02;          // beyond this the a^4 term of the core series matters
 
-struct G1Row { float c0, c1, c2, c3; };
+struct alignas(16) G1Row { float c0, c1, c2, c3; };
 
 #if defined(__CUDACC__)
 static __device__ const G1Row g1_tab_dev[MCALF_G1_N] = { MCALF_G1_ROWS };
@@ -114,18 +114,20 @@ MCALF_HD float depth32(float x) {
     return fma32(-sc.f, r * q, 1.0f - sc.f);
 }
 
-MCALF_HD G1Row g1_row(int j) {
+// tab: the table's copy in shared memory (kernels), or null for the global/host copy
+MCALF_HD G1Row g1_row(int j, const G1Row *tab = nullptr) {
 #if defined(__CUDA_ARCH__)
-    const float4 v = __ldg(reinterpret_cast<const float4 *>(g1_tab_dev) + j);
+    const float4 v = tab ? reinterpret_cast<const float4 *>(tab)[j] : __ldg(reinterpret_cast<const float4 *>(g1_tab_dev) + j);
     G1Row r; r.c0 = v.x; r.c1 = v.y; r.c2 = v.z; r.c3 = v.w;
     return r;
 #else
+    (void)tab;
     return g1_tab_host[j];
 #endif
 }
 
 // Line-core H(a,u) for u given as a two-float (uh + ul), s = u^2+a^2 < S_CUT, a <= A_MAX_FAST.
-MCALF_HD float core_h32(float a, float a2, float uh, float ul) {
+MCALF_HD float core_h32(float a, float a2, float uh, float ul, const G1Row *tab = nullptr) {
     float x = uh * uh;
     float xlo = fma32(uh, uh, -x) + 2.0f * uh * ul;
     float g0 = exp_neg32(x, xlo);
@@ -135,7 +137,7 @@ MCALF_HD float core_h32(float a, float a2, float uh, float ul) {
     int j = (int)fj;
     j = j < MCALF_G1_N - 1 ? j : MCALF_G1_N - 1;
     float d = fma32(fj, -1.0f / (float)MCALF_G1_INV_H, au) + sl;
-    G1Row t = g1_row(j);
+    G1Row t = g1_row(j, tab);
     float g1 = fma32(fma32(fma32(t.c3, d, t.c2), d, t.c1), d, t.c0);
     float k0 = fma32(a2, fma32(-2.0f, x, 1.0f), 1.0f);
     float k1 = fma32(a2, fma32(-0.666666687f, x, 1.0f), 1.0f);
@@ -157,7 +159,7 @@ MCALF_HD float ex2_32(float t) {
 // Gaussian through MUFU.EX2 (relative error 2^-22).  The optical-depth error is <= ~3e-7 tau, i.e. a
 // flux error <= 1.5e-7 for kappa <= KAPPA_LEAN (the flux sensitivity F |dtau| peaks near tau = 1).
 constexpr float KAPPA_LEAN = 8.0f;
-MCALF_HD float core_h32_lean(float a, float a2, float u) {
+MCALF_HD float core_h32_lean(float a, float a2, float u, const G1Row *tab = nullptr) {
     const float x = u * u;
     const float g0 = ex2_32(x * -1.44269504088896341f);
     const float au = fabsf(u);
@@ -165,7 +167,7 @@ MCALF_HD float core_h32_lean(float a, float a2, float u) {
     int j = (int)fj;
     j = j < MCALF_G1_N - 1 ? j : MCALF_G1_N - 1;
     const float d = fma32(fj, -1.0f / (float)MCALF_G1_INV_H, au);
-    const G1Row t = g1_row(j);
+    const G1Row t = g1_row(j, tab);
     const float g1 = fma32(fma32(fma32(t.c3, d, t.c2), d, t.c1), d, t.c0);
     const float k0 = fma32(a2, fma32(-2.0f, x, 1.0f), 1.0f);
     const float k1 = fma32(a2, fma32(-0.666666687f, x, 1.0f), 1.0f);
