@@ -206,3 +206,93 @@ def test_full_size_properties():
     Pq = g.prior_transform_batch(U[:4])
     ref = np.array([o.lnlhood_worker(p) for p in Pq])
     logl_close(logl[:4], ref, C)
+
+
+def _random_problem(seed):
+    """A small random problem: odd pixel counts, 1-3 windows (possibly with gaps), random line sets,
+    free/fixed specres and continuum, fillers, NaN / zero-error pixels."""
+    rng = np.random.default_rng(seed)
+    names = list(orc.ATOMIC)
+    lines = list(rng.choice(names, size=rng.integers(1, 5), replace=False))
+    w0 = orc.ATOMIC[lines[0]][0]
+    z0 = rng.uniform(1.5, 3.5)
+    centre = w0 * (1 + z0)
+    nwin = int(rng.integers(1, 4))
+    velstep = rng.uniform(0.7, 3.0)
+    waves, fitrange = [], []
+    lam = centre * (1 - 400.0 / orc.C_KMS * rng.uniform(0.5, 1.5))
+    for _ in range(nwin):
+        n = int(rng.integers(3, 700))
+        if rng.random() < 0.5:
+            seg = lam * np.exp(np.arange(n) * velstep / orc.C_KMS)            # log-uniform
+        else:
+            seg = lam + np.arange(n) * lam * velstep / orc.C_KMS              # linear in wavelength
+        waves.append(seg)
+        fitrange.append((seg[0] - 1e-3, seg[-1] + 1e-3))
+        lam = seg[-1] * (1 + rng.uniform(0.0005, 0.003))
+    wave = np.concatenate(waves)
+    flux = 1.0 + rng.normal(0, 0.03, wave.size)
+    err = rng.uniform(0.01, 0.05, wave.size)
+    if rng.random() < 0.5:
+        flux[rng.integers(0, wave.size)] = np.nan
+        err[rng.integers(0, wave.size)] = 0.0
+    ncmax = int(rng.integers(0, 6))
+    kw = dict(fitrange=fitrange, fitlines=lines, ncomp=(int(rng.integers(0, ncmax + 1)), ncmax), nfill=int(rng.integers(0, 3)),
+              specres=[4.0, 14.0] if rng.random() < 0.6 else [float(rng.uniform(0.3, 12.0))],
+              contval=[0.8, 1.2] if rng.random() < 0.5 else [1.0], Nrange=(11.5, 15.5), brange=(1.5, 45.0),
+              zrange=(z0 - 0.002, z0 + 0.004))
+    return (wave, flux, err), kw
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_small_problems(seed):
+    import mcalf_b200
+    spec, kw = _random_problem(seed)
+    o = orc.OracleFitter(spec, **kw)
+    g = mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                              **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                 if k not in ("fitrange", "fitlines", "ncomp")})
+    assert g.velstep == pytest.approx(o.velstep, rel=1e-14)
+    U = np.random.default_rng(1000 + seed).random((48, o.ndim))
+    P = np.array([o._scale_cube_pc(u) for u in U])
+    assert np.array_equal(g.prior_transform_batch(U), P)
+    with np.errstate(all="ignore"):
+        ref = np.array([o.lnlhood_worker(p) for p in P])
+    got = g.lnlhood_batch(U, unit_cube=True)
+    logl_close(got, ref, const_term(o))
+    assert np.allclose(g.lnlhood_batch(P, fp64=True), ref, rtol=1e-9)
+    flux = g.reconstruct_spec_batch(P[:6])
+    for i in range(6):
+        assert np.abs(flux[i] - o.reconstruct_spec(P[i])).max() / abs(o.unpack(P[i])[1]) <= FLUX_TOL
+
+
+def test_long_spectrum_many_chunks():
+    """More chunks than lanes (20000 px = 79 chunks) and more lines than one slot list row."""
+    import mcalf_b200
+    rng = np.random.default_rng(3)
+    wave = 5000.0 * np.exp(np.arange(20001) * 1.3 / orc.C_KMS)
+    spec = (wave, 1.0 + rng.normal(0, 0.02, wave.size), np.full(wave.size, 0.02))
+    lines = ["CIV 1548", "CIV 1550", "SiIV 1393", "SiIV 1402"]
+    kw = dict(fitrange=[(wave[0] - 1, wave[-1] + 1)], fitlines=lines, ncomp=(25, 25), nfill=1, specres=[5.0, 9.0],
+              contval=[0.95, 1.05], Nrange=(12.0, 14.8), brange=(4.0, 35.0), zrange=(2.30, 2.46))
+    o = orc.OracleFitter(spec, **kw)
+    g = mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], lines, list(kw["ncomp"]),
+                              **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                 if k not in ("fitrange", "fitlines", "ncomp")})
+    assert g.geometry()["nchunks"] > 64
+    U = np.random.default_rng(8).random((6, o.ndim))
+    P = np.array([o._scale_cube_pc(u) for u in U])
+    ref = np.array([o.lnlhood_worker(p) for p in P])
+    logl_close(g.lnlhood_batch(P), ref, const_term(o))
+    flux = g.reconstruct_spec_batch(P[:2])
+    for i in range(2):
+        assert np.abs(flux[i] - o.reconstruct_spec(P[i])).max() / abs(o.unpack(P[i])[1]) <= FLUX_TOL
+
+
+def test_problem_too_large_is_refused():
+    import mcalf_b200
+    wave = 4000.0 * np.exp(np.arange(120000) * 1.0 / orc.C_KMS)
+    spec = (wave, np.ones(wave.size), np.full(wave.size, 0.02))
+    with pytest.raises(mcalf_b200.capi.McalfError) as ei:
+        mcalf_b200.als_fitter(spec, [[wave[0] - 1, wave[-1] + 1]], ["CIV 1548"], [1, 1])
+    assert ei.value.code == mcalf_b200.capi.E_RESOURCE
