@@ -302,9 +302,16 @@ def run_ours(args):
             sm_max = 1965.0
         peak_nominal = geo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
         achieved = flop / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:   # dram__bytes_read + dram__bytes_write of this kernel at this batch size, from the committed ncu capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if tr.get("batch") == B:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except (OSError, ValueError, KeyError):
+            pass
         roofline = {
             "bound": "fp32_alu", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
-            "traffic": None,
+            "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic: %d)" % (B * (g.ndim * 8 + 8)),
             "peak_source": "FFMA-only microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry)",
             "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
             "kernel": "mcalf_fast_kernel", "kernel_ms": kernel_ms, "flop_per_logL": flop / B,
