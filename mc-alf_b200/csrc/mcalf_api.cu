@@ -89,11 +89,12 @@ int choose_launch(mcalf_ctx *c) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
     size_t smem = fast_smem_bytes(P, nwarps);
-    while (smem > (size_t)prop.sharedMemPerBlockOptin && nwarps > 1) {
+    const size_t static_smem = 3200;   // the kernel's fixed-address H1 table
+    while (smem + static_smem > (size_t)prop.sharedMemPerBlockOptin && nwarps > 1) {
         nwarps = (nwarps + 1) / 2;
         smem = fast_smem_bytes(P, nwarps);
     }
-    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+    if (smem + static_smem > (size_t)prop.sharedMemPerBlockOptin)
         return fail(MCALF_E_RESOURCE, "problem needs %zu B of shared memory per CTA (limit %zu): too many pixels/lines", smem,
                     (size_t)prop.sharedMemPerBlockOptin);
     c->smem_fp64 = fp64_smem_bytes(P);
@@ -104,7 +105,7 @@ int choose_launch(mcalf_ctx *c) {
     c->smem_fast = smem;
     CU(configure_kernels(c->smem_fast, c->smem_fp64));
     int occ = 0;
-    CU(fast_occupancy(c->threads, c->smem_fast, &occ));
+    CU(fast_occupancy(c->threads, c->smem_fast, &occ));   // accounts for the kernel's static shared memory too
     if (occ < 1) return fail(MCALF_E_RESOURCE, "fp32 kernel does not fit an SM (threads %d, smem %zu)", c->threads, smem);
     c->ctas_per_sm = c->ctas_opt > 0 ? std::min(c->ctas_opt, occ) : occ;
     return MCALF_OK;

@@ -151,7 +151,6 @@ struct FastSmem {
     int2 *wl;          // [nchunks][nslots][list_cap]  near lines of a chunk: {line | core << 16, U_hi bits}
     float *farp;       // [nchunks][FF_NC * nslots + 1] partial far-field coefficients, [n][slot] within a chunk
     int *cnt;          // [nchunks][nslots]            entries in each sub-list | core entries << 16
-    G1Row *g1;         // [MCALF_G1_N] Taylor rows of H1 (line-core form)
     float *taps;       // [2*nmax4 + 8]
     float *flux;       // [halo + npix4 + halo + 8]
     double *red;       // [64]
@@ -170,7 +169,6 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     s.wl = (int2 *)take(sizeof(int2) * (size_t)P.nchunks * P.nslots * P.list_cap);
     s.farp = (float *)take(sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
     s.cnt = (int *)take(sizeof(int) * (size_t)P.nchunks * P.nslots);
-    s.g1 = (G1Row *)take(sizeof(G1Row) * MCALF_G1_N);
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
@@ -188,7 +186,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     FastSmem S = carve(smem_raw, P);
     const uint32_t flags = Bt.flags;
 
-    for (int i = tid; i < MCALF_G1_N; i += nthreads) S.g1[i] = g1_tab_dev[i];
+    __shared__ G1Row g1_smem[MCALF_G1_N];       // Taylor rows of H1 (line-core form), fixed address
+    for (int i = tid; i < MCALF_G1_N; i += nthreads) g1_smem[i] = g1_tab_dev[i];
     // per-thread statistics (only summed when Bt.stats != nullptr)
     unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0;
 
@@ -313,10 +312,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             }
             // near lines, direct wing form: 8 evaluations per lane per line; inside a line core the
             // clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
-            int ncore = 0;
+            unsigned coremask = 0;           // slots (at most 32) that listed a line core for this chunk
             for (int sidx = 0; sidx < NS; ++sidx) {
                 const int cc = S.cnt[c * NS + sidx];
-                ncore += cc >> 16;
+                coremask |= (cc >> 16) ? (1u << sidx) : 0u;
                 const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
                 for (int e = 0; e < (cc & 0xffff); ++e) {
                     const int2 E = list[e];
@@ -330,17 +329,18 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     }
                 }
             }
-            // line cores: only the 32-pixel rows a core can reach.  The row index is dynamic, so the
-            // contributions are accumulated in shared memory -- in the chunk's own (still unused)
-            // slice of the depth buffer -- and added to the register-resident tau afterwards.
-            if (ncore) {
+            // line cores: only the pixels a core can reach.  The pixel index is dynamic, so tau is parked
+            // in shared memory for this pass -- in the chunk's own (still unused) slice of the depth
+            // buffer -- the cores are accumulated there, and tau comes back to registers afterwards.
+            if (coremask) {
                 float *tcore = S.flux + P.halo + cd.start;
 #pragma unroll
                 for (int j = 0; j < PX; ++j)
-                    if (j * 32 + lane < cd.len) tcore[j * 32 + lane] = 0.0f;
-                for (int sidx = 0; sidx < NS; ++sidx) {
+                    if (j * 32 + lane < cd.len) tcore[j * 32 + lane] = tau[j];
+                __syncwarp();
+                for (unsigned rem = coremask; rem; rem &= rem - 1) {
+                    const int sidx = __ffs(rem) - 1;
                     const int cc = S.cnt[c * NS + sidx];
-                    if (!(cc >> 16)) continue;
                     const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
                     for (int e = 0; e < (cc & 0xffff); ++e) {
                         const int2 E = list[e];
@@ -368,7 +368,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                                 const bool ca = fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
                                 const float uca = ua + fma32(L.A_hi, da.y, fma32(L.A_lo, da.x, Ul));
                                 const float ucb = ub + fma32(L.A_hi, db.y, fma32(L.A_lo, db.x, Ul));
-                                const float ha = core_h32_lean(L.a, L.a2, uca, S.g1), hb = core_h32_lean(L.a, L.a2, ucb, S.g1);
+                                const float ha = core_h32_lean(L.a, L.a2, uca, g1_smem), hb = core_h32_lean(L.a, L.a2, ucb, g1_smem);
                                 if (ca) ta_p[0] = ta + fma32(L.kappa, ha, -L.c1w);
                                 if (cb) ta_p[32] = tb + fma32(L.kappa, hb, -L.c1w);
                                 if (STATS) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
@@ -382,16 +382,17 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                                 if (s < S_CUT) {
                                     float uh, ul;
                                     core_u2(L.A_hi, L.A_lo, dk.x, dk.y, Uh, Ul, uh, ul);
-                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul, S.g1), -L.c1w);
+                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul, g1_smem), -L.c1w);
                                     if (STATS) { st_core += 1; st_corep += 1; }
                                 }
                             }
                         }
                     }
                 }
+                __syncwarp();
 #pragma unroll
                 for (int j = 0; j < PX; ++j)
-                    if (j * 32 + lane < cd.len) tau[j] += tcore[j * 32 + lane];
+                    if (j * 32 + lane < cd.len) tau[j] = tcore[j * 32 + lane];
             }
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
