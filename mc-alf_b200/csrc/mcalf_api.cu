@@ -383,7 +383,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
         P.cslot_lw = lw;
         P.vwarps = std::max(1, 8 / (32 / w));      // about eight slots whatever the chunk count
         P.nslots = P.vwarps * (32 / w);
-        P.list_cap = (P.Lmax + P.nslots - 1) / P.nslots;
+        P.mwords = (P.Lmax + 31) / 32;
     }
 
     std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),

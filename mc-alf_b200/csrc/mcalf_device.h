@@ -15,7 +15,7 @@ struct DevProblem {
     int ncompmax, nfill, ndim, ndim_pad;
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
-    int Lmax, list_cap;                 // list_cap: entries per (chunk, slot) sub-list
+    int Lmax, mwords;                   // mwords: 32-bit words of a per-chunk line mask, ceil(Lmax / 32)
     int cslot_w, cslot_lw, nslots, vwarps; // lanes per chunk group (power of two), its log2, slots = vwarps * 32 / cslot_w
     float eps_cull, eps_far;
     double fixed_specres, fixed_cont, velstep, lam_ref;

@@ -148,9 +148,10 @@ struct FastSmem {
     double *A64;       // [Lmax]
     double *rc64;      // [Lmax]
     LineP *lp;         // [Lmax]
-    int2 *wl;          // [nchunks][nslots][list_cap]  near lines of a chunk: {line | core << 16, U_hi bits}
+    float *uarr;       // [nchunks][Lmax]     U_hi of the near (line, chunk) pairs
+    unsigned *nmask;   // [nchunks][mwords]   bit t: line t is near chunk c (evaluated in the direct form)
+    unsigned *cmask;   // [nchunks][mwords]   bit t: the core of line t may reach chunk c
     float *farp;       // [nchunks][FF_NC * nslots + 1] partial far-field coefficients, [n][slot] within a chunk
-    int *cnt;          // [nchunks][nslots]            entries in each sub-list | core entries << 16
     float *taps;       // [2*nmax4 + 8]
     float *flux;       // [halo + npix4 + halo + 8]
     double *red;       // [64]
@@ -166,9 +167,10 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     s.A64 = (double *)take(sizeof(double) * P.Lmax);
     s.rc64 = (double *)take(sizeof(double) * P.Lmax);
     s.lp = (LineP *)take(sizeof(LineP) * P.Lmax);
-    s.wl = (int2 *)take(sizeof(int2) * (size_t)P.nchunks * P.nslots * P.list_cap);
+    s.uarr = (float *)take(sizeof(float) * (size_t)P.nchunks * P.Lmax);
+    s.nmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
+    s.cmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
     s.farp = (float *)take(sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
-    s.cnt = (int *)take(sizeof(int) * (size_t)P.nchunks * P.nslots);
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
@@ -217,6 +219,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // outside the fp32 path's domain: damping too large, or anything non-finite / non-positive
             if (!(L.a <= P.a_max) || !(L.A > 0.0) || !(L.A < 1e30) || !(L.kappa < 1e30) || !(L.kappa >= 0.0)) bad = 1;
         }
+        for (int i = tid; i < P.nchunks * P.mwords; i += nthreads) { S.nmask[i] = 0u; S.cmask[i] = 0u; }
         int n4 = 0;
         if (warp == nwarps - 1) {
             n4 = build_taps(P, h.specres, S.taps, lane);
@@ -234,24 +237,24 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         n4 = S.misc[2];
 
         // ---- pass A: classify every (line, chunk) pair, lane = chunk ----
-        // Far pairs fold into per-(chunk, slot) partial expansions, near pairs are listed per
-        // (chunk, slot).  A slot is one lane group of one of P.vwarps virtual warps and owns the lines
-        // slot, slot + nslots, ...; sums and lists are later read in slot order.
+        // Far pairs fold into per-(chunk, slot) partial expansions (a slot is one lane group of one of
+        // P.vwarps virtual warps and owns the lines slot, slot + nslots, ...; the partials are later
+        // summed in slot order).  Near pairs set bit `line` of the chunk's near mask (and core mask) and
+        // leave their U: pass B walks the masks in line order, so nothing depends on who classified what.
         {
-            const int W = P.cslot_w, LW = P.cslot_lw, SUB = 32 >> LW, NS = P.nslots, CAP = P.list_cap;
+            const int W = P.cslot_w, LW = P.cslot_lw, SUB = 32 >> LW, NS = P.nslots, MW = P.mwords;
             const int fstride = FF_NC * NS + 1;
             for (int vw = warp; vw < P.vwarps; vw += nwarps) {
                 const int slot = vw * SUB + (lane >> LW);
                 for (int cg = 0; cg < P.nchunks; cg += W) {
                     const int c = cg + (lane & (W - 1));
                     const bool cact = c < P.nchunks;
-                    const double rho_s = P.chunks[cact ? c : 0].rho_s;
-                    const float ds = P.chunks[cact ? c : 0].ds;
+                    const int cs = cact ? c : 0;
+                    const double rho_s = P.chunks[cs].rho_s;
+                    const float ds = P.chunks[cs].ds;
                     float C[FF_NC];
 #pragma unroll
                     for (int n = 0; n < FF_NC; ++n) C[n] = 0.0f;
-                    int nw = 0, nc = 0;
-                    int2 *list = S.wl + ((size_t)(cact ? c : 0) * NS + slot) * CAP;
                     for (int t = slot; t < h.nact; t += NS) {
                         const double U = S.A64[t] * (rho_s - S.rc64[t]);
                         const float Uh = (float)U;
@@ -259,8 +262,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, P.eps_cull, P.eps_far) : -1;
                         if (cls == 3) farfield_accumulate(L.x, Uh, ds, L.z, L.y, C);
                         if (cls == 1 || cls == 2) {
-                            list[nw++] = make_int2(t | (cls == 2 ? 0x10000 : 0), __float_as_int(Uh));
-                            nc += cls == 2;
+                            S.uarr[cs * P.Lmax + t] = Uh;
+                            atomicOr(&S.nmask[cs * MW + (t >> 5)], 1u << (t & 31));
+                            if (cls == 2) atomicOr(&S.cmask[cs * MW + (t >> 5)], 1u << (t & 31));
                         }
                         if (STATS) {
                             const int len = cact ? P.chunks[c].len : 0;
@@ -275,7 +279,6 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         float *fp = S.farp + (size_t)c * fstride + slot;
 #pragma unroll
                         for (int n = 0; n < FF_NC; ++n) fp[n * NS] = C[n];
-                        S.cnt[c * NS + slot] = nw | (nc << 16);
                     }
                 }
             }
@@ -291,7 +294,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
             const ChunkDesc cd = P.chunks[c];
-            const int NS = P.nslots, CAP = P.list_cap;
+            const int NS = P.nslots;
             float d[PX], tau[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
@@ -310,17 +313,16 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < PX; ++j) tau[j] = farfield_eval(C, d[j] * cd.inv_ds);
             }
-            // near lines, direct wing form: 8 evaluations per lane per line; inside a line core the
-            // clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
-            unsigned coremask = 0;           // slots (at most 32) that listed a line core for this chunk
-            for (int sidx = 0; sidx < NS; ++sidx) {
-                const int cc = S.cnt[c * NS + sidx];
-                coremask |= (cc >> 16) ? (1u << sidx) : 0u;
-                const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
-                for (int e = 0; e < (cc & 0xffff); ++e) {
-                    const int2 E = list[e];
-                    const float4 L = *reinterpret_cast<const float4 *>(&S.lp[E.x & 0xffff]);   // A_hi, a2, c1, kappa
-                    const float Uh = __int_as_float(E.y);
+            // near lines, direct wing form, in line order: 8 evaluations per lane per line; inside a line
+            // core the clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
+            const int MW = P.mwords;
+            unsigned anycore = 0;
+            for (int w = 0; w < MW; ++w) {
+                anycore |= S.cmask[c * MW + w];
+                for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
+                    const int t = (w << 5) + __ffs(m) - 1;
+                    const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
+                    const float Uh = S.uarr[c * P.Lmax + t];
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
                         const float u = fma32(L.x, d[j], Uh);
@@ -332,25 +334,29 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // line cores: only the pixels a core can reach.  The pixel index is dynamic, so tau is parked
             // in shared memory for this pass -- in the chunk's own (still unused) slice of the depth
             // buffer -- the cores are accumulated there, and tau comes back to registers afterwards.
-            if (coremask) {
+            if (anycore) {
                 float *tcore = S.flux + P.halo + cd.start;
 #pragma unroll
                 for (int j = 0; j < PX; ++j)
                     if (j * 32 + lane < cd.len) tcore[j * 32 + lane] = tau[j];
                 __syncwarp();
-                for (unsigned rem = coremask; rem; rem &= rem - 1) {
-                    const int sidx = __ffs(rem) - 1;
-                    const int cc = S.cnt[c * NS + sidx];
-                    const int2 *list = S.wl + ((size_t)c * NS + sidx) * CAP;
-                    for (int e = 0; e < (cc & 0xffff); ++e) {
-                        const int2 E = list[e];
-                        if (!(E.x & 0x10000)) continue;
-                        const int t = E.x & 0xffff;
-                        const LineP L = S.lp[t];
-                        float Uh, Ul;
-                        split2(S.A64[t] * (cd.rho_s - S.rc64[t]), Uh, Ul);
-                        int k_lo, k_hi;
-                        core_range(cd, L.iA, Uh, k_lo, k_hi);
+                for (int w = 0; w < MW; ++w) {
+                    unsigned cm = S.cmask[c * MW + w];
+                    if (!cm) continue;
+                    // lane l prepares line 32 w + l (fp64 offset, its low part, the pixel range) ...
+                    float myUh = 0.f, myUl = 0.f;
+                    int myklo = 0, mykhi = -1;
+                    if ((cm >> lane) & 1u) {
+                        const int tl = (w << 5) + lane;
+                        split2(S.A64[tl] * (cd.rho_s - S.rc64[tl]), myUh, myUl);
+                        core_range(cd, S.lp[tl].iA, myUh, myklo, mykhi);
+                    }
+                    // ... and the warp takes the lines one at a time
+                    for (; cm; cm &= cm - 1) {
+                        const int src = __ffs(cm) - 1;
+                        const float Uh = __shfl_sync(0xffffffffu, myUh, src), Ul = __shfl_sync(0xffffffffu, myUl, src);
+                        const int k_lo = __shfl_sync(0xffffffffu, myklo, src), k_hi = __shfl_sync(0xffffffffu, mykhi, src);
+                        const LineP L = S.lp[(w << 5) + src];
                         const float2 *dd = P.delta2 + cd.start;
                         if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
                             // branch-free, 64 consecutive pixels per trip (two per lane in flight): the
