@@ -39,6 +39,7 @@ constexpr int NBUF = 2;
 constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
 constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
 constexpr double A_MAX_LIMIT = 0.02;
+constexpr int FF_NC_HOST = 6;          // far-field coefficients per chunk (FF_DEG + 1 in voigt_math.cuh)
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -60,7 +61,7 @@ struct mcalf_ctx {
     std::vector<void *> allocs;
     Slot slot[NBUF];
     unsigned long long *d_stats = nullptr;
-    int threads = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0;
+    int threads = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
     size_t smem_fast = 0, smem_fp64 = 0;
     long long slice = 16384;
     int collect_stats = 0;
@@ -104,8 +105,13 @@ int choose_launch(mcalf_ctx *c) {
     c->threads = nwarps * 32;
     c->smem_fast = smem;
     CU(configure_kernels(c->smem_fast, c->smem_fp64));
-    int occ = 0;
-    CU(fast_occupancy(c->threads, c->smem_fast, &occ));   // accounts for the kernel's static shared memory too
+    int occ = 0, occ_dense = 0;
+    CU(fast_occupancy(c->threads, c->smem_fast, 0, &occ));   // accounts for the kernel's static shared memory too
+    if (c->threads <= 256 && c->dense_opt == 1) CU(fast_occupancy(c->threads, c->smem_fast, 1, &occ_dense));
+    // measured (cfg 2-4): the kernel is issue bound, a fifth CTA does not pay for the 48-register build's
+    // spills, so it is used only on request
+    c->dense = (c->dense_opt == 1 && occ_dense >= 1) ? 1 : 0;
+    if (c->dense) occ = occ_dense;
     if (occ < 1) return fail(MCALF_E_RESOURCE, "fp32 kernel does not fit an SM (threads %d, smem %zu)", c->threads, smem);
     c->ctas_per_sm = c->ctas_opt > 0 ? std::min(c->ctas_opt, occ) : occ;
     return MCALF_OK;
@@ -186,7 +192,7 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
         c->samples_fp64 += (uint64_t)n;
     } else {
         const int grid = (int)std::min<long long>(n, (long long)c->sm_count * c->ctas_per_sm);
-        CU(launch_fast(c->P, a, grid, c->threads, c->smem_fast, st));
+        CU(launch_fast(c->P, a, grid, c->threads, c->smem_fast, c->dense, st));
         // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
         // (exits at once when the list is empty)
         const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);
@@ -384,6 +390,9 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
         P.vwarps = std::max(1, 8 / (32 / w));      // about eight slots whatever the chunk count
         P.nslots = P.vwarps * (32 / w);
         P.mwords = (P.Lmax + 31) / 32;
+        int minlen = 1 << 30;
+        for (const ChunkDesc &cd : chunks) minlen = std::min(minlen, cd.len);
+        P.scratch_in_flux = minlen >= (FF_NC_HOST * P.nslots + 1) + P.Lmax + 32 ? 1 : 0;   // + the bank skew
     }
 
     std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),
@@ -578,6 +587,9 @@ int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
         if (value < 0) return fail(MCALF_E_INVALID, "ctas_per_sm must be >= 0");
         c->ctas_opt = (int)value;
         return choose_launch(c);
+    } else if (!strcmp(name, "dense")) {
+        c->dense_opt = value < 0 ? -1 : (value != 0.0);
+        return choose_launch(c);
     } else if (!strcmp(name, "slice")) {
         if (value < 1) return fail(MCALF_E_INVALID, "slice must be >= 1");
         c->slice = (long long)value;
@@ -595,6 +607,7 @@ int mcalf_get_option(mcalf_ctx *c, const char *name, double *value) {
     else if (!strcmp(name, "collect_stats")) *value = c->collect_stats;
     else if (!strcmp(name, "threads")) *value = c->threads;
     else if (!strcmp(name, "ctas_per_sm")) *value = c->ctas_per_sm;
+    else if (!strcmp(name, "dense")) *value = c->dense;
     else if (!strcmp(name, "slice")) *value = (double)c->slice;
     else return fail(MCALF_E_INVALID, "unknown option '%s'", name);
     return MCALF_OK;

@@ -16,6 +16,7 @@ struct DevProblem {
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
     int Lmax, mwords;                   // mwords: 32-bit words of a per-chunk line mask, ceil(Lmax / 32)
+    int scratch_in_flux, pad2_;          // pass-A outputs of a chunk live in its slice of the depth buffer
     int cslot_w, cslot_lw, nslots, vwarps; // lanes per chunk group (power of two), its log2, slots = vwarps * 32 / cslot_w
     float eps_cull, eps_far;
     double fixed_specres, fixed_cont, velstep, lam_ref;
@@ -47,8 +48,8 @@ struct BatchArgs {
 size_t fast_smem_bytes(const DevProblem &P, int nwarps);
 size_t fp64_smem_bytes(const DevProblem &P);
 cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes);
-cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm);
-cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st);
 cudaError_t launch_fp64(const DevProblem &P, const BatchArgs &Bt, const int *idx_list, const unsigned int *idx_count, int grid,
                         size_t smem, cudaStream_t st);
 cudaError_t launch_prior(const DevProblem &P, const double *cube, long long B, long long ld, uint32_t flags, double *out,

@@ -148,6 +148,8 @@ struct FastSmem {
     double *A64;       // [Lmax]
     double *rc64;      // [Lmax]
     LineP *lp;         // [Lmax]
+    // uarr and farp live in the chunk's own slice of `flux` instead (which nothing else uses until pass B
+    // writes the chunk's depth) when every chunk is long enough: P.scratch_in_flux
     float *uarr;       // [nchunks][Lmax]     U_hi of the near (line, chunk) pairs
     unsigned *nmask;   // [nchunks][mwords]   bit t: line t is near chunk c (evaluated in the direct form)
     unsigned *cmask;   // [nchunks][mwords]   bit t: the core of line t may reach chunk c
@@ -167,10 +169,10 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     s.A64 = (double *)take(sizeof(double) * P.Lmax);
     s.rc64 = (double *)take(sizeof(double) * P.Lmax);
     s.lp = (LineP *)take(sizeof(LineP) * P.Lmax);
-    s.uarr = (float *)take(sizeof(float) * (size_t)P.nchunks * P.Lmax);
+    s.uarr = (float *)take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * P.Lmax);
     s.nmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
     s.cmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
-    s.farp = (float *)take(sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
+    s.farp = (float *)take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
     s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
     s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
     s.red = (double *)take(sizeof(double) * 64);
@@ -179,8 +181,8 @@ MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
     return s;
 }
 
-template <bool STATS>
-__global__ void __launch_bounds__(1024, 1)
+template <bool STATS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
 mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ BatchArgs Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,6 +254,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const int cs = cact ? c : 0;
                     const double rho_s = P.chunks[cs].rho_s;
                     const float ds = P.chunks[cs].ds;
+                    float *fslice = P.scratch_in_flux ? S.flux + P.halo + P.chunks[cs].start + (cs & 31) : S.farp + (size_t)cs * fstride;   // skewed: lanes hit distinct banks
+                    float *uslice = P.scratch_in_flux ? fslice + fstride : S.uarr + (size_t)cs * P.Lmax;
                     float C[FF_NC];
 #pragma unroll
                     for (int n = 0; n < FF_NC; ++n) C[n] = 0.0f;
@@ -262,7 +266,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, P.eps_cull, P.eps_far) : -1;
                         if (cls == 3) farfield_accumulate(L.x, Uh, ds, L.z, L.y, C);
                         if (cls == 1 || cls == 2) {
-                            S.uarr[cs * P.Lmax + t] = Uh;
+                            uslice[t] = Uh;
                             atomicOr(&S.nmask[cs * MW + (t >> 5)], 1u << (t & 31));
                             if (cls == 2) atomicOr(&S.cmask[cs * MW + (t >> 5)], 1u << (t & 31));
                         }
@@ -276,9 +280,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         }
                     }
                     if (cact) {
-                        float *fp = S.farp + (size_t)c * fstride + slot;
 #pragma unroll
-                        for (int n = 0; n < FF_NC; ++n) fp[n * NS] = C[n];
+                        for (int n = 0; n < FF_NC; ++n) fslice[n * NS + slot] = C[n];
                     }
                 }
             }
@@ -295,6 +298,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (c >= P.nchunks) break;
             const ChunkDesc cd = P.chunks[c];
             const int NS = P.nslots;
+            const float *fslice = P.scratch_in_flux ? S.flux + P.halo + cd.start + (c & 31) : S.farp + (size_t)c * (FF_NC * NS + 1);
+            const float *uslice = P.scratch_in_flux ? fslice + (FF_NC * NS + 1) : S.uarr + (size_t)c * P.Lmax;
             float d[PX], tau[PX];
 #pragma unroll
             for (int j = 0; j < PX; ++j) {
@@ -304,7 +309,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // far lines: sum the slots' partial expansions in slot order (lane n sums coefficient n),
             // broadcast, one polynomial per pixel
             {
-                const float *fp = S.farp + (size_t)c * (FF_NC * NS + 1) + (lane < FF_NC ? lane : 0) * NS;
+                const float *fp = fslice + (lane < FF_NC ? lane : 0) * NS;
                 float cn = 0.0f;
                 for (int sidx = 0; sidx < NS; ++sidx) cn += fp[sidx];
                 float C[FF_NC];
@@ -322,7 +327,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
                     const int t = (w << 5) + __ffs(m) - 1;
                     const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
-                    const float Uh = S.uarr[c * P.Lmax + t];
+                    const float Uh = uslice[t];
 #pragma unroll
                     for (int j = 0; j < PX; ++j) {
                         const float u = fma32(L.x, d[j], Uh);
@@ -678,20 +683,25 @@ size_t fp64_smem_bytes(const DevProblem &P) {
 }
 
 cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mcalf_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    cudaError_t e = cudaFuncSetAttribute(mcalf_fast_kernel<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mcalf_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    e = cudaFuncSetAttribute(mcalf_fast_kernel<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(mcalf_fast_kernel<false, 256, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(mcalf_fp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp64_bytes);
 }
 
-cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false>, threads, smem);
+// dense = the 48-register build (CTAs of at most 256 threads, five or more per SM)
+cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm) {
+    if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, 256, 5>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, 1024, 1>, threads, smem);
 }
 
-cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st) {
-    if (Bt.stats) mcalf_fast_kernel<true><<<grid, threads, smem, st>>>(P, Bt);
-    else mcalf_fast_kernel<false><<<grid, threads, smem, st>>>(P, Bt);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st) {
+    if (Bt.stats) mcalf_fast_kernel<true, 1024, 1><<<grid, threads, smem, st>>>(P, Bt);
+    else if (dense && threads <= 256) mcalf_fast_kernel<false, 256, 5><<<grid, threads, smem, st>>>(P, Bt);
+    else mcalf_fast_kernel<false, 1024, 1><<<grid, threads, smem, st>>>(P, Bt);
     return cudaGetLastError();
 }
 
