@@ -84,7 +84,7 @@ int upload(mcalf_ctx *c, const std::vector<T> &v, const T **out) {
 
 int choose_launch(mcalf_ctx *c) {
     const DevProblem &P = c->P;
-    int nwarps = c->threads_opt > 0 ? c->threads_opt / 32 : std::min(std::max(P.nchunks, 2), 8);
+    int nwarps = c->threads_opt > 0 ? c->threads_opt / 32 : std::min(std::max((P.nchunks + 1) / 2, 2), 8);   // measured: about two chunks per warp balances best
     if (nwarps < 1) nwarps = 1;
     if (nwarps > 32) nwarps = 32;
     cudaDeviceProp prop;
