@@ -164,7 +164,7 @@ def run_reference(args):
     if rank != 0:
         return
     pool, cores = cpu_pool()
-    n = max(cores * 4, 64)
+    n = max(cores * 32, 512)      # ~20 s of CPU work per step on one core's clock, spread over the cores
     U = unit_cube(n, 63, 0)
     for _ in range(args.warmup):
         cpu_time(pool, cores, U[:cores])
@@ -326,7 +326,7 @@ def run_ours(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             pool, cores = cpu_pool()
-            ncpu = max(cores * 4, 64)
+            ncpu = max(cores * 32, 512)          # ~20 s of CPU work in total
             tcpu = cpu_time(pool, cores, Uh[:ncpu])
             pool.close()
             cpu = {"value": ncpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",

@@ -296,3 +296,23 @@ def test_problem_too_large_is_refused():
     with pytest.raises(mcalf_b200.capi.McalfError) as ei:
         mcalf_b200.als_fitter(spec, [[wave[0] - 1, wave[-1] + 1]], ["CIV 1548"], [1, 1])
     assert ei.value.code == mcalf_b200.capi.E_RESOURCE
+
+
+def test_bench_size_batch_fp32_vs_fp64_kernel():
+    """BASELINE cfg 4 at the bench's own batch size (262144 unit-cube vectors): the fp32 kernel against
+    the fp64 check kernel (itself tied to the oracle at 1e-10 above) on 4096 randomly chosen samples of
+    that batch, plus the size-independent properties on the whole batch."""
+    o, g = fitters("cfg4")
+    B = 262144
+    U = np.random.default_rng(4000).random((B, o.ndim))
+    logl, chi2 = g.lnlhood_batch(U, unit_cube=True, return_chi2=True)
+    assert np.isfinite(logl).all()
+    C = const_term(o)
+    assert np.allclose(logl, C - 0.5 * chi2, rtol=1e-14)
+    pick = np.random.default_rng(1).choice(B, size=4096, replace=False)
+    ref = g.lnlhood_batch(U[pick], unit_cube=True, fp64=True)
+    worst = logl_close(logl[pick], ref, C)
+    assert np.array_equal(g.lnlhood_batch(U[pick], unit_cube=True), logl[pick])    # batch composition is irrelevant
+    st = g.stats()
+    assert st["samples_fp64"] == 4096            # nothing of the fp32 batch was silently re-routed
+    print("bench-size batch: worst relative logL difference fp32 vs fp64 kernel %.2e" % worst)
