@@ -63,7 +63,7 @@ struct mcalf_ctx {
     unsigned long long *d_stats = nullptr;
     int threads = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
     size_t smem_fast = 0, smem_fp64 = 0;
-    long long slice = 16384;
+    long long slice = 32768;
     int collect_stats = 0;
     uint64_t kernel_launches = 0, samples = 0, samples_fp64 = 0;
     int last_slot = -1;
