@@ -229,6 +229,8 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     // host pointers: slices pipelined through two pinned staging slots, one stream each, so the
     // H2D of slice k+1 and the D2H of slice k-1 overlap the kernel of slice k
     long long slice = c->slice;
+    // pageable input: the staging memcpy runs on this thread, so smaller slices overlap it better with the kernels
+    if (!is_pinned(params)) slice = std::min<long long>(slice, 8192);
     if (flux) slice = std::max<long long>(1, std::min<long long>(slice, (long long)((64u << 20) / ((size_t)c->P.npix * esize))));
     slice = std::min(slice, B);
     const size_t flux_bytes = flux ? (size_t)slice * c->P.npix * esize : 0;
