@@ -61,7 +61,7 @@ struct mcalf_ctx {
     std::vector<void *> allocs;
     Slot slot[NBUF];
     unsigned long long *d_stats = nullptr;
-    int threads = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
+    int threads = 0, threads_small = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
     size_t smem_fast = 0, smem_fp64 = 0;
     long long slice = 32768;
     int collect_stats = 0;
@@ -114,6 +114,12 @@ int choose_launch(mcalf_ctx *c) {
     if (c->dense) occ = occ_dense;
     if (occ < 1) return fail(MCALF_E_RESOURCE, "fp32 kernel does not fit an SM (threads %d, smem %zu)", c->threads, smem);
     c->ctas_per_sm = c->ctas_opt > 0 ? std::min(c->ctas_opt, occ) : occ;
+    c->threads_small = 0;
+    {
+        const int ts = 32 * std::min(std::max(P.nchunks, 1), 32);
+        int occ_s = 0;
+        if (ts > c->threads && fast_occupancy(ts, c->smem_fast, 0, &occ_s) == cudaSuccess && occ_s >= 1) c->threads_small = ts;
+    }
     return MCALF_OK;
 }
 
@@ -191,8 +197,12 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
         c->kernel_launches += 1;
         c->samples_fp64 += (uint64_t)n;
     } else {
-        const int grid = (int)std::min<long long>(n, (long long)c->sm_count * c->ctas_per_sm);
-        CU(launch_fast(c->P, a, grid, c->threads, c->smem_fast, c->dense, st));
+        int grid = (int)std::min<long long>(n, (long long)c->sm_count * c->ctas_per_sm);
+        int threads = c->threads;
+        // fewer samples than SMs: one CTA per sample, as many warps as the sample has chunks (results do
+        // not depend on the CTA size)
+        if (n <= c->sm_count && c->threads_opt == 0 && c->threads_small > threads) threads = c->threads_small;
+        CU(launch_fast(c->P, a, grid, threads, c->smem_fast, threads == c->threads ? c->dense : 0, st));
         // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
         // (exits at once when the list is empty)
         const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);

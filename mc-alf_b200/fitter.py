@@ -461,8 +461,22 @@ class als_fitter:
             return +np.inf, []
         return float(self.chi2_batch(row[None, :])[0])
 
+    def _scalar_buffers(self):
+        b = getattr(self, "_sb", None)
+        if b is None:
+            row, out = np.empty((1, self.ndim), dtype=np.float64), np.empty(1, dtype=np.float64)
+            b = self._sb = (row, out, row.ctypes.data, out.ctypes.data)
+        return b
+
     def lnlhood_worker(self, p):                                         # :287-328
-        return float(self.lnlhood_batch(self._row(p)[None, :])[0])
+        # batch of one through preallocated buffers: this is the call a CPU sampler makes per point
+        row, out, prow, pout = self._scalar_buffers()
+        try:
+            row[0, :] = p
+        except (TypeError, ValueError):
+            row[0, :] = [p[x] for x in range(self.ndim)]
+        capi.check(self._lib.mcalf_loglike_batch(self._ctx, prow, 1, self.ndim, self._flags(), None, pout, None))
+        return float(out[0])
 
     def lnlhood_pc(self, p):                                             # :250-262
         return self.lnlhood_worker(p), []
@@ -470,8 +484,11 @@ class als_fitter:
     def lnlhood_dy(self, p):                                             # :264-272
         return self.lnlhood_worker(p)
 
-    def lnlhood_mn(self, p, ndim, nparam):                               # :274-285 (p may be a ctypes double*)
-        return float(self.lnlhood_batch(self._row(p, ndim)[None, :])[0])
+    def lnlhood_mn(self, p, ndim, nparam):                               # :274-285 (p is a ctypes double* under MultiNest)
+        row, out, prow, pout = self._scalar_buffers()
+        row[0, :] = [p[x] for x in range(self.ndim)]
+        capi.check(self._lib.mcalf_loglike_batch(self._ctx, prow, 1, self.ndim, self._flags(), None, pout, None))
+        return float(out[0])
 
     def __call__(self, p):                                               # :509-518 (the reference calls a missing self.lnlhood)
         lp = self.lnprior(p)
