@@ -240,13 +240,15 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     // H2D of slice k+1 and the D2H of slice k-1 overlap the kernel of slice k
     long long slice = c->slice;
     // pageable input: the staging memcpy runs on this thread, so smaller slices overlap it better with the kernels
-    if (!is_pinned(params)) slice = std::min<long long>(slice, 8192);
+    if (B > 8192 && !is_pinned(params)) slice = std::min<long long>(slice, 8192);
     if (flux) slice = std::max<long long>(1, std::min<long long>(slice, (long long)((64u << 20) / ((size_t)c->P.npix * esize))));
     slice = std::min(slice, B);
     const size_t flux_bytes = flux ? (size_t)slice * c->P.npix * esize : 0;
     // caller buffers that are already page-locked (mcalf_host_alloc, torch pin_memory) skip the staging copy
-    const bool pin_in = is_pinned(params);
-    const bool pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2), pin_flux = is_pinned(flux);
+    // (small calls are always staged: the pointer queries would cost more than the copies)
+    const bool small = (size_t)B * (size_t)ld * sizeof(double) <= (64u << 10) && !flux;
+    const bool pin_in = !small && is_pinned(params);
+    const bool pin_logl = !small && is_pinned(logl), pin_chi2 = !small && is_pinned(chi2), pin_flux = !small && is_pinned(flux);
     struct Pending { long long off = 0, n = 0; bool live = false; } pend[NBUF];
     auto drain = [&](int k) -> int {
         Slot &s = c->slot[k];
