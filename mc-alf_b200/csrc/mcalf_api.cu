@@ -36,6 +36,7 @@ int fail(int code, const char *fmt, ...) {
     } while (0)
 
 constexpr int NBUF = 2;
+constexpr int NRING = 3;
 constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
 constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
 constexpr double A_MAX_LIMIT = 0.02;
@@ -60,13 +61,18 @@ struct mcalf_ctx {
     DevProblem P{};
     std::vector<void *> allocs;
     Slot slot[NBUF];
+    Slot ring[NRING];                 // the copy-stream / compute-stream pipeline of large logL calls
+    cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
+    cudaEvent_t ring_h2d[NRING] = {nullptr, nullptr, nullptr};
+    double *pipe_dout = nullptr, *pipe_hout = nullptr;
+    size_t pipe_dout_cap = 0, pipe_hout_cap = 0;
     unsigned long long *d_stats = nullptr;
     int threads = 0, threads_small = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
     size_t smem_fast = 0, smem_fp64 = 0;
-    long long slice = 32768;
+    long long slice = 65536;
     int collect_stats = 0;
     uint64_t kernel_launches = 0, samples = 0, samples_fp64 = 0;
-    int last_slot = -1;
+    int last_slot = -1, last_ring = -1;
 };
 
 namespace {
@@ -233,7 +239,61 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         int rc = ensure_slot(c, s, B, ld, 0, false);
         if (rc) return rc;
         c->last_slot = 0;
+        c->last_ring = -1;
         return enqueue(c, s, (cudaStream_t)stream, params, B, ld, flags, logl, chi2, flux);
+    }
+
+    // Large logL / chi2 calls: one copy stream feeds a ring of device slices, one compute stream runs the
+    // kernels back to back; only the first slice's H2D is exposed, and the results come back in one copy.
+    if (!flux && B > c->slice) {
+        const long long slice = c->slice;
+        const bool pin_in = is_pinned(params), pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2);
+        if (!c->copy_stream) {
+            CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
+            for (int r = 0; r < NRING; ++r) CU(cudaEventCreateWithFlags(&c->ring_h2d[r], cudaEventDisableTiming));
+        }
+        const size_t obytes = sizeof(double) * 2 * (size_t)B;
+        if (obytes > c->pipe_dout_cap) {
+            if (c->pipe_dout) CU(cudaFree(c->pipe_dout));
+            CU(cudaMalloc((void **)&c->pipe_dout, obytes));
+            c->pipe_dout_cap = obytes;
+        }
+        if ((!pin_logl || (chi2 && !pin_chi2)) && obytes > c->pipe_hout_cap) {
+            if (c->pipe_hout) CU(cudaFreeHost(c->pipe_hout));
+            CU(cudaMallocHost((void **)&c->pipe_hout, obytes));
+            c->pipe_hout_cap = obytes;
+        }
+        double *d_logl = c->pipe_dout, *d_chi2 = c->pipe_dout + B;
+        long long k = 0, n = 0;
+        for (long long off = 0; off < B; off += n, ++k) {
+            // ramp the first slices up (4096, 8192, ...): only the first H2D is exposed, so keep it short
+            n = std::min(std::min(slice, (long long)4096 << std::min<long long>(k, 8)), B - off);
+            const int r = (int)(k % NRING);
+            Slot &s = c->ring[r];
+            int rc = ensure_slot(c, s, slice, ld, 0, true);
+            if (rc) return rc;
+            if (k >= NRING) CU(cudaEventSynchronize(s.done));          // the ring slot's previous slice has been consumed
+            const double *src = params + off * ld;
+            if (!pin_in) {
+                memcpy(s.h_params, src, sizeof(double) * (size_t)n * (size_t)ld);
+                src = s.h_params;
+            }
+            CU(cudaMemcpyAsync(s.d_params, src, sizeof(double) * (size_t)n * (size_t)ld, cudaMemcpyHostToDevice, c->copy_stream));
+            CU(cudaEventRecord(c->ring_h2d[r], c->copy_stream));
+            CU(cudaStreamWaitEvent(c->comp_stream, c->ring_h2d[r], 0));
+            rc = enqueue(c, s, c->comp_stream, s.d_params, n, ld, flags, logl ? d_logl + off : nullptr, chi2 ? d_chi2 + off : nullptr, nullptr);
+            if (rc) return rc;
+            CU(cudaEventRecord(s.done, c->comp_stream));
+            c->last_slot = -1;
+            c->last_ring = r;
+        }
+        if (logl) CU(cudaMemcpyAsync(pin_logl ? logl : c->pipe_hout, d_logl, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->comp_stream));
+        if (chi2) CU(cudaMemcpyAsync(pin_chi2 ? chi2 : c->pipe_hout + B, d_chi2, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, c->comp_stream));
+        CU(cudaStreamSynchronize(c->comp_stream));
+        if (logl && !pin_logl) memcpy(logl, c->pipe_hout, sizeof(double) * (size_t)B);
+        if (chi2 && !pin_chi2) memcpy(chi2, c->pipe_hout + B, sizeof(double) * (size_t)B);
+        return MCALF_OK;
     }
 
     // host pointers: slices pipelined through two pinned staging slots, one stream each, so the
@@ -286,6 +346,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         pend[k].n = n;
         pend[k].live = true;
         c->last_slot = k;
+        c->last_ring = -1;
     }
     for (int j = 0; j < NBUF; ++j) {
         int rc = drain(j);
@@ -451,6 +512,23 @@ void mcalf_destroy(mcalf_ctx *c) {
         if (s.k1) cudaEventDestroy(s.k1);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    for (Slot &s : c->ring) {
+        if (s.h_params) cudaFreeHost(s.h_params);
+        if (s.d_params) cudaFree(s.d_params);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.counters) cudaFree(s.counters);
+        if (s.fallback) cudaFree(s.fallback);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.k0) cudaEventDestroy(s.k0);
+        if (s.k1) cudaEventDestroy(s.k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    for (int r = 0; r < NRING; ++r) if (c->ring_h2d[r]) cudaEventDestroy(c->ring_h2d[r]);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->comp_stream) cudaStreamDestroy(c->comp_stream);
+    if (c->pipe_dout) cudaFree(c->pipe_dout);
+    if (c->pipe_hout) cudaFreeHost(c->pipe_hout);
     for (void *d : c->allocs) cudaFree(d);
     if (c->d_stats) cudaFree(c->d_stats);
     delete c;
@@ -559,9 +637,9 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     out->evals_culled = h[4];
     out->evals_far = h[5];
     out->evals_core_precise = h[6];
-    if (c->last_slot >= 0) {
+    if (c->last_slot >= 0 || c->last_ring >= 0) {
         float ms = 0.f;
-        Slot &s = c->slot[c->last_slot];
+        Slot &s = c->last_slot >= 0 ? c->slot[c->last_slot] : c->ring[c->last_ring];
         if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->last_kernel_ms = ms;
     }
     return MCALF_OK;
