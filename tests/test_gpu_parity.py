@@ -316,3 +316,31 @@ def test_bench_size_batch_fp32_vs_fp64_kernel():
     st = g.stats()
     assert st["samples_fp64"] == 4096            # nothing of the fp32 batch was silently re-routed
     print("bench-size batch: worst relative logL difference fp32 vs fp64 kernel %.2e" % worst)
+
+
+def test_damped_and_saturated_lines():
+    """Column densities far above the BASELINE priors (sub-DLA / DLA Lyman-alpha, logN 17-21): damping
+    wings fill the window, tau reaches 1e7 at the core; nothing may take a form it is not valid for."""
+    import mcalf_b200
+    rng = np.random.default_rng(11)
+    wave = 4700.0 * np.exp(np.arange(6000) * 2.0 / orc.C_KMS)
+    spec = (wave, 1.0 + rng.normal(0, 0.02, wave.size), np.full(wave.size, 0.02))
+    kw = dict(fitrange=[(wave[0] - 1, wave[-1] + 1)], fitlines=["HI 1215", "HI 1025"], ncomp=(3, 3), nfill=0,
+              specres=[6.0, 12.0], contval=[1.0], Nrange=(12.0, 21.0), brange=(5.0, 60.0), zrange=(2.92, 2.98))
+    o = orc.OracleFitter(spec, **kw)
+    g = mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                              **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                 if k not in ("fitrange", "fitlines", "ncomp")})
+    P = np.array([[8.0, 3, 20.3, 2.95, 30.0, 17.2, 2.93, 12.0, 13.5, 2.97, 8.0],
+                  [7.0, 3, 21.0, 2.94, 55.0, 19.0, 2.96, 20.0, 18.0, 2.925, 5.0],
+                  [11.0, 3, 18.5, 2.95, 40.0, 16.0, 2.951, 7.0, 14.2, 2.9495, 25.0],
+                  [9.0, 2, 19.7, 2.975, 15.0, 12.3, 2.93, 33.0, 20.0, 2.95, 10.0]])
+    ref = np.array([o.lnlhood_worker(p) for p in P])
+    logl_close(g.lnlhood_batch(P), ref, const_term(o))
+    assert np.allclose(g.lnlhood_batch(P, fp64=True), ref, rtol=1e-9)
+    flux = g.reconstruct_spec_batch(P)
+    for i in range(len(P)):
+        assert np.abs(flux[i] - o.reconstruct_spec(P[i])).max() <= FLUX_TOL
+    U = np.random.default_rng(12).random((64, o.ndim))
+    Pd = np.array([o._scale_cube_pc(u) for u in U])
+    logl_close(g.lnlhood_batch(Pd), np.array([o.lnlhood_worker(p) for p in Pd]), const_term(o))
