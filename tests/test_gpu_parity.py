@@ -344,3 +344,24 @@ def test_damped_and_saturated_lines():
     U = np.random.default_rng(12).random((64, o.ndim))
     Pd = np.array([o._scale_cube_pc(u) for u in U])
     logl_close(g.lnlhood_batch(Pd), np.array([o.lnlhood_worker(p) for p in Pd]), const_term(o))
+
+
+def test_multi_device_fitter_single_process():
+    """Several context replicas driven from host threads of one process (all visible GPUs; two replicas
+    on the same GPU when there is only one) return exactly what a single context returns."""
+    import torch
+    from mcalf_b200.multi import MultiDeviceFitter
+    spec, kw, _ = case("cfg2")
+    o, g = fitters("cfg2")
+    ndev = torch.cuda.device_count()
+    devices = list(range(ndev)) if ndev > 1 else [0, 0]
+    m = MultiDeviceFitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]), devices=devices,
+                          **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                             if k not in ("fitrange", "fitlines", "ncomp")})
+    U = np.random.default_rng(21).random((1001, o.ndim))
+    assert np.array_equal(m.lnlhood_batch(U, unit_cube=True), g.lnlhood_batch(U, unit_cube=True))
+    assert np.array_equal(m.prior_transform_batch(U[:7]), g.prior_transform_batch(U[:7]))
+    assert np.array_equal(m.reconstruct_spec_batch(U[:5], unit_cube=True), g.reconstruct_spec_batch(U[:5], unit_cube=True))
+    assert m.ndim == g.ndim and m.lnlhood_dy(g._scale_cube_pc(U[0])) == g.lnlhood_dy(g._scale_cube_pc(U[0]))
+    assert m.lnlhood_batch(U[:1], unit_cube=True).shape == (1,)
+    m.close()
