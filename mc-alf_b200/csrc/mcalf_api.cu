@@ -225,6 +225,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     if (!c) return fail(MCALF_E_INVALID, "null context");
     if (B < 0) return fail(MCALF_E_INVALID, "negative batch size");
     if (B == 0) return MCALF_OK;
+    if (B > (1LL << 30)) return fail(MCALF_E_INVALID, "batch of %lld rows: split calls above 2^30 rows", B);
     if (!params) return fail(MCALF_E_INVALID, "null params");
     const int need = (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) ? 5 : c->P.ndim;
     if (ld < need) return fail(MCALF_E_INVALID, "ld (%lld) smaller than the row length (%d)", ld, need);
@@ -382,6 +383,10 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     CU(cudaSetDevice(device));
 
     mcalf_ctx *c = new mcalf_ctx();
+    struct Guard {                      // every early error return below releases the half-built context
+        mcalf_ctx *p;
+        ~Guard() { if (p) mcalf_destroy(p); }
+    } guard{c};
     c->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
@@ -478,8 +483,8 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     std::vector<double> blo(p->bounds_lo, p->bounds_lo + ndim), bhi(p->bounds_hi, p->bounds_hi + ndim);
 
     int rc;
-#define UPF4(vec, field) { const float *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) { mcalf_destroy(c); return rc; } P.field = reinterpret_cast<const float4 *>(tmp_); }
-#define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) { mcalf_destroy(c); return rc; }
+#define UPF4(vec, field) { const float *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) return rc; P.field = reinterpret_cast<const float4 *>(tmp_); }
+#define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) return rc;
     std::vector<float2> d2(npix + 64, make_float2(0.f, 0.f));      // padded: the core pass reads 32 ahead unguarded
     for (int i = 0; i < npix; ++i) d2[i] = make_float2(dhi[i], dlo[i]);
     UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
@@ -488,8 +493,9 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
 #undef UPF4
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
-    if (e != cudaSuccess) { mcalf_destroy(c); return fail(MCALF_E_CUDA, "stats buffer: %s", cudaGetErrorString(e)); }
-    if ((rc = choose_launch(c)) != MCALF_OK) { mcalf_destroy(c); return rc; }
+    if (e != cudaSuccess) return fail(MCALF_E_CUDA, "stats buffer: %s", cudaGetErrorString(e));
+    if ((rc = choose_launch(c)) != MCALF_OK) return rc;
+    guard.p = nullptr;
     *out = c;
     return MCALF_OK;
 }
