@@ -43,12 +43,12 @@ WORKLOAD = "cfg4: 8192 px x 20 comps x 2 lines (CIV doublet), free specres+conti
 # executed FP32 flops per unit of each path of mcalf_fast_kernel (FMA = 2, add/mul/min/max/rint = 1,
 # MUFU = 1); derivation in DESIGN.md section 5
 FLOP_PAIR_CLASS = 18     # chunk_class per (line, chunk) pair
-FLOP_PAIR_FAR = 58       # farfield_accumulate per far pair
+FLOP_PAIR_FAR = 74       # farfield_accumulate per far pair (8 coefficients x 3 series)
 FLOP_NEAR_EVAL = 17      # direct wing form per (line, pixel) of a near (wing or mixed) pair
 FLOP_CORE_LEAN = 38      # extra per line-core pixel, weak line
 FLOP_CORE_PRECISE = 75   # extra per line-core pixel, strong line (two-float coordinate, polynomial exp)
-FLOP_CHUNK = 48          # summing the slots' far-field partials, per (sample, chunk)
-FLOP_PIXEL = 44          # far-field polynomial (11) + depth32 (23) + residual / chi-square (10); stencil: 2 per padded tap
+FLOP_CHUNK = 64          # summing the slots' far-field partials, per (sample, chunk)
+FLOP_PIXEL = 48          # far-field polynomial (15) + depth32 (23) + residual / chi-square (10); stencil: 2 per padded tap
 CHUNK = 256
 # SURVEY 8d canonical counts (Weideman-32 core, 3-term asymptotic wing)
 CANON_EVAL = 5.0

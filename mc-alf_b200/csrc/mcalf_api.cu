@@ -40,7 +40,7 @@ constexpr int NRING = 3;
 constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
 constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
 constexpr double A_MAX_LIMIT = 0.02;
-constexpr int FF_NC_HOST = 6;          // far-field coefficients per chunk (FF_DEG + 1 in voigt_math.cuh)
+constexpr int FF_NC_HOST = 8;          // far-field coefficients per chunk (FF_DEG + 1 in voigt_math.cuh)
 
 struct Slot {
     cudaStream_t stream = nullptr;

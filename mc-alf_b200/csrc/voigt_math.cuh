@@ -304,7 +304,7 @@ constexpr float U_CORE_MARGIN = 6.01f;
 // per pixel.  A (line, chunk) pair takes this form only if the proven error bound
 //   c1/umin^2 [ 2 (FF_DEG+2) r^(FF_DEG+1)/(1-FF_RMAX)^2 + 14/umin^6 ] <= eps_far
 // holds (umin = |U| - A ds, the closest approach), so strong or nearby lines stay on the direct form.
-constexpr int FF_DEG = 5;
+constexpr int FF_DEG = 7;
 constexpr float FF_RMAX = 0.45f;
 constexpr float FF_UMIN = 10.0f;
 constexpr float FF_TRUNC = 2.0f * (FF_DEG + 2) / ((1.0f - 0.45f) * (1.0f - 0.45f));
@@ -323,7 +323,10 @@ MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float eps_c
     if (r <= FF_RMAX && umin >= FF_UMIN) {
         const float r2 = r * r;
         const float iu2 = rcp32(um2);
-        const float err = c1 * iu2 * fma32(FF_TRUNC, r2 * r2 * r2, 14.0f * iu2 * iu2 * iu2);
+        float rp = r2 * r2;                          // r^(FF_DEG + 1), FF_DEG odd
+#pragma unroll
+        for (int k = 4; k < FF_DEG + 1; k += 2) rp *= r2;
+        const float err = c1 * iu2 * fma32(FF_TRUNC, rp, 14.0f * iu2 * iu2 * iu2);
         if (err <= eps_far) return 3;
     }
     return 1;
@@ -338,8 +341,9 @@ MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, fl
     const float T2 = T1 * v * (1.5f - a2);
     const float T3 = T1 * v * v * 3.75f;
     // binom(-2,n) = (-1)^n (n+1), binom(-4,n) = (-1)^n C(n+3,3), binom(-6,n) = (-1)^n C(n+5,5)
-    const float b2[6] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f};
-    const float b3[6] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f};
+    const float b2[10] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f, 84.f, 120.f, 165.f, 220.f};
+    const float b3[10] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f, 462.f, 792.f, 1287.f, 2002.f};
+    static_assert(FF_DEG % 2 == 1 && FF_DEG <= 9, "chunk_class computes r^(FF_DEG+1) by squaring; tables hold 10 binomials");
     float sn = 1.0f;
 #pragma unroll
     for (int n = 0; n <= FF_DEG; ++n) {
