@@ -37,6 +37,8 @@ int fail(int code, const char *fmt, ...) {
 
 constexpr int NBUF = 2;
 constexpr int NRING = 3;
+constexpr size_t ZC_PARAM_BYTES = 256u << 10;  // zero-copy path: at most 256 KB of parameters ...
+constexpr long long ZC_MAX_ROWS = 1024;       // ... and 1024 rows
 constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
 constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
 constexpr double A_MAX_LIMIT = 0.02;
@@ -49,7 +51,8 @@ struct Slot {
     double *h_out = nullptr, *d_out = nullptr;         // 2 * slice doubles (logL, chi2)
     void *h_flux = nullptr, *d_flux = nullptr;
     size_t flux_cap = 0, params_cap = 0, out_cap = 0;
-    unsigned int *counters = nullptr;                  // [2]: work counter, fallback count
+    unsigned int *counters = nullptr;                  // [2][2]: {work counter, fallback count} x launch parity
+    int parity = 0;
     int *fallback = nullptr;                           // [fallback_cap]
     size_t fallback_cap = 0;
 };
@@ -61,10 +64,13 @@ struct mcalf_ctx {
     DevProblem P{};
     std::vector<void *> allocs;
     Slot slot[NBUF];
+    Slot dev_slot;                    // counters / fallback list of the MCALF_F_ON_DEVICE path
     Slot ring[NRING];                 // the copy-stream / compute-stream pipeline of large logL calls
     cudaStream_t copy_stream = nullptr, comp_stream = nullptr;
     cudaEvent_t ring_h2d[NRING] = {nullptr, nullptr, nullptr};
     double *pipe_dout = nullptr, *pipe_hout = nullptr;
+    double *zc_buf = nullptr;         // mapped pinned memory for small host calls: params in, results out, no copies
+    Slot zc_slot;
     size_t pipe_dout_cap = 0, pipe_hout_cap = 0;
     unsigned long long *d_stats = nullptr;
     int threads = 0, threads_small = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
@@ -135,7 +141,8 @@ int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_by
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
         CU(cudaEventCreate(&s.k0));
         CU(cudaEventCreate(&s.k1));
-        CU(cudaMalloc((void **)&s.counters, 2 * sizeof(unsigned int)));
+        CU(cudaMalloc((void **)&s.counters, 4 * sizeof(unsigned int)));
+        CU(cudaMemset(s.counters, 0, 4 * sizeof(unsigned int)));
     }
     if ((size_t)n > s.fallback_cap) {
         if (s.fallback) CU(cudaFree(s.fallback));
@@ -191,11 +198,13 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
     a.logl_out = d_logl;
     a.chi2_out = d_chi2;
     a.flux_out = d_flux;
-    a.work_counter = s.counters;
-    a.fallback_count = s.counters + 1;
+    // the fast kernel of launch k clears the counter pair launch k+1 will use: no memset per call
+    unsigned int *cnt = s.counters + 2 * s.parity;
+    a.work_counter = cnt;
+    a.fallback_count = cnt + 1;
+    a.clear_counters = s.counters + 2 * (s.parity ^ 1);
     a.fallback_list = s.fallback;
     a.stats = c->collect_stats ? c->d_stats : nullptr;
-    CU(cudaMemsetAsync(s.counters, 0, 2 * sizeof(unsigned int), st));
     CU(cudaEventRecord(s.k0, st));
     const int fp64_grid = (int)std::min<long long>(n, (long long)c->sm_count * 8);
     if (flags & MCALF_F_FP64) {
@@ -212,8 +221,9 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
         // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
         // (exits at once when the list is empty)
         const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);
-        CU(launch_fp64(c->P, a, s.fallback, s.counters + 1, fgrid, c->smem_fp64, st));
+        CU(launch_fp64(c->P, a, s.fallback, cnt + 1, fgrid, c->smem_fp64, st));
         c->kernel_launches += 2;
+        s.parity ^= 1;
     }
     CU(cudaEventRecord(s.k1, st));
     c->samples += (uint64_t)n;
@@ -236,12 +246,31 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     const size_t esize = (flags & MCALF_F_FLUX_F64) ? 8 : 4;
 
     if (flags & MCALF_F_ON_DEVICE) {
-        Slot &s = c->slot[0];
+        Slot &s = c->dev_slot;
         int rc = ensure_slot(c, s, B, ld, 0, false);
         if (rc) return rc;
-        c->last_slot = 0;
+        c->last_slot = NBUF;             // = dev_slot
         c->last_ring = -1;
         return enqueue(c, s, (cudaStream_t)stream, params, B, ld, flags, logl, chi2, flux);
+    }
+
+    // Small calls (the scalar callbacks of a CPU sampler, one live set): the kernel reads the parameters
+    // from, and writes the results to, mapped pinned host memory -- no copy operations, one stream sync.
+    if (!flux && (size_t)B * (size_t)ld * sizeof(double) <= ZC_PARAM_BYTES && B <= ZC_MAX_ROWS) {
+        Slot &s = c->zc_slot;
+        int rc = ensure_slot(c, s, ZC_MAX_ROWS, ld, 0, false);
+        if (rc) return rc;
+        if (!c->zc_buf) CU(cudaHostAlloc((void **)&c->zc_buf, ZC_PARAM_BYTES + 2 * ZC_MAX_ROWS * sizeof(double), cudaHostAllocMapped));
+        double *zp = c->zc_buf, *zo = c->zc_buf + ZC_PARAM_BYTES / sizeof(double);
+        memcpy(zp, params, sizeof(double) * (size_t)B * (size_t)ld);
+        c->last_slot = NBUF + 1;         // = zc_slot
+        c->last_ring = -1;
+        rc = enqueue(c, s, s.stream, zp, B, ld, flags, logl ? zo : nullptr, chi2 ? zo + ZC_MAX_ROWS : nullptr, nullptr);
+        if (rc) return rc;
+        CU(cudaStreamSynchronize(s.stream));
+        if (logl) memcpy(logl, zo, sizeof(double) * (size_t)B);
+        if (chi2) memcpy(chi2, zo + ZC_MAX_ROWS, sizeof(double) * (size_t)B);
+        return MCALF_OK;
     }
 
     // Large logL / chi2 calls: one copy stream feeds a ring of device slices, one compute stream runs the
@@ -518,6 +547,17 @@ void mcalf_destroy(mcalf_ctx *c) {
         if (s.k1) cudaEventDestroy(s.k1);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    if (c->zc_buf) cudaFreeHost(c->zc_buf);
+    for (Slot *sp : {&c->dev_slot, &c->zc_slot}) {
+        Slot &s = *sp;
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.counters) cudaFree(s.counters);
+        if (s.fallback) cudaFree(s.fallback);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.k0) cudaEventDestroy(s.k0);
+        if (s.k1) cudaEventDestroy(s.k1);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
     for (Slot &s : c->ring) {
         if (s.h_params) cudaFreeHost(s.h_params);
         if (s.d_params) cudaFree(s.d_params);
@@ -645,7 +685,7 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     out->evals_core_precise = h[6];
     if (c->last_slot >= 0 || c->last_ring >= 0) {
         float ms = 0.f;
-        Slot &s = c->last_slot >= 0 ? c->slot[c->last_slot] : c->ring[c->last_ring];
+        Slot &s = c->last_slot == NBUF + 1 ? c->zc_slot : c->last_slot == NBUF ? c->dev_slot : (c->last_slot >= 0 ? c->slot[c->last_slot] : c->ring[c->last_ring]);
         if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->last_kernel_ms = ms;
     }
     return MCALF_OK;

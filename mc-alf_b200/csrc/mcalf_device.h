@@ -39,8 +39,9 @@ struct BatchArgs {
     uint32_t flags, pad_;
     double *logl_out, *chi2_out;
     void *flux_out;
-    unsigned int *work_counter;         // zeroed before the launch
-    unsigned int *fallback_count;       // zeroed before the launch
+    unsigned int *work_counter;         // zero at launch (cleared by the previous launch, see clear_counters)
+    unsigned int *fallback_count;       // zero at launch
+    unsigned int *clear_counters;       // [2] the counter pair of the NEXT launch on this slot: this launch zeroes it
     int *fallback_list;                 // [B]
     unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far, core-precise} evaluations
 };

@@ -192,6 +192,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 
     __shared__ G1Row g1_smem[MCALF_G1_N];       // Taylor rows of H1 (line-core form), fixed address
     for (int i = tid; i < MCALF_G1_N; i += nthreads) g1_smem[i] = g1_tab_dev[i];
+    if (blockIdx.x == 0 && tid == 0) { Bt.clear_counters[0] = 0u; Bt.clear_counters[1] = 0u; }   // for the slot's next launch
     // per-thread statistics (only summed when Bt.stats != nullptr)
     unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0;
 
