@@ -53,6 +53,8 @@ struct Slot {
     size_t flux_cap = 0, params_cap = 0, out_cap = 0;
     unsigned int *counters = nullptr;                  // [2][2]: {work counter, fallback count} x launch parity
     int parity = 0;
+    BatchArgs pending{};                               // the last deferred fix-up (zero-copy path)
+    unsigned int *pending_count = nullptr;
     int *fallback = nullptr;                           // [fallback_cap]
     size_t fallback_cap = 0;
 };
@@ -188,8 +190,10 @@ bool is_pinned(const void *p) {
 }
 
 // enqueue the kernels of one slice on `st`; all pointers are device pointers
+// fallback_flag (mapped host memory, nullable): when given, the fp64 fix-up kernel is NOT launched here; the
+// caller synchronises, looks at the flag and calls enqueue_fixup only if a sample was re-routed
 int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long long n, long long ld, uint32_t flags,
-            double *d_logl, double *d_chi2, void *d_flux) {
+            double *d_logl, double *d_chi2, void *d_flux, int *fallback_flag = nullptr) {
     BatchArgs a{};
     a.params = d_params;
     a.B = n;
@@ -204,6 +208,7 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
     a.fallback_count = cnt + 1;
     a.clear_counters = s.counters + 2 * (s.parity ^ 1);
     a.fallback_list = s.fallback;
+    a.fallback_flag = fallback_flag;
     a.stats = c->collect_stats ? c->d_stats : nullptr;
     CU(cudaEventRecord(s.k0, st));
     const int fp64_grid = (int)std::min<long long>(n, (long long)c->sm_count * 8);
@@ -220,10 +225,16 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
         CU(launch_fast(c->P, a, grid, threads, c->smem_fast, threads == c->threads ? c->dense : 0, st));
         // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
         // (exits at once when the list is empty)
-        const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);
-        CU(launch_fp64(c->P, a, s.fallback, cnt + 1, fgrid, c->smem_fp64, st));
-        c->kernel_launches += 2;
+        c->kernel_launches += 1;
         s.parity ^= 1;
+        if (!fallback_flag) {
+            const int fgrid = (int)std::min<long long>(n, (long long)c->sm_count * 2);
+            CU(launch_fp64(c->P, a, s.fallback, cnt + 1, fgrid, c->smem_fp64, st));
+            c->kernel_launches += 1;
+        } else {
+            s.pending = a;               // for enqueue_fixup
+            s.pending_count = cnt + 1;
+        }
     }
     CU(cudaEventRecord(s.k1, st));
     c->samples += (uint64_t)n;
@@ -260,14 +271,23 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         Slot &s = c->zc_slot;
         int rc = ensure_slot(c, s, ZC_MAX_ROWS, ld, 0, false);
         if (rc) return rc;
-        if (!c->zc_buf) CU(cudaHostAlloc((void **)&c->zc_buf, ZC_PARAM_BYTES + 2 * ZC_MAX_ROWS * sizeof(double), cudaHostAllocMapped));
+        if (!c->zc_buf) CU(cudaHostAlloc((void **)&c->zc_buf, ZC_PARAM_BYTES + 2 * ZC_MAX_ROWS * sizeof(double) + 64, cudaHostAllocMapped));
         double *zp = c->zc_buf, *zo = c->zc_buf + ZC_PARAM_BYTES / sizeof(double);
+        int *zflag = (int *)(zo + 2 * ZC_MAX_ROWS);
+        *zflag = 0;
         memcpy(zp, params, sizeof(double) * (size_t)B * (size_t)ld);
         c->last_slot = NBUF + 1;         // = zc_slot
         c->last_ring = -1;
-        rc = enqueue(c, s, s.stream, zp, B, ld, flags, logl ? zo : nullptr, chi2 ? zo + ZC_MAX_ROWS : nullptr, nullptr);
+        rc = enqueue(c, s, s.stream, zp, B, ld, flags, logl ? zo : nullptr, chi2 ? zo + ZC_MAX_ROWS : nullptr, nullptr,
+                     (flags & MCALF_F_FP64) ? nullptr : zflag);
         if (rc) return rc;
         CU(cudaStreamSynchronize(s.stream));
+        if (*zflag) {                    // rare: some sample lies outside the fp32 kernel's domain
+            const int fgrid = (int)std::min<long long>(B, (long long)c->sm_count * 2);
+            CU(launch_fp64(c->P, s.pending, s.fallback, s.pending_count, fgrid, c->smem_fp64, s.stream));
+            c->kernel_launches += 1;
+            CU(cudaStreamSynchronize(s.stream));
+        }
         if (logl) memcpy(logl, zo, sizeof(double) * (size_t)B);
         if (chi2) memcpy(chi2, zo + ZC_MAX_ROWS, sizeof(double) * (size_t)B);
         return MCALF_OK;

@@ -43,6 +43,7 @@ struct BatchArgs {
     unsigned int *fallback_count;       // zero at launch
     unsigned int *clear_counters;       // [2] the counter pair of the NEXT launch on this slot: this launch zeroes it
     int *fallback_list;                 // [B]
+    int *fallback_flag;                 // nullable, mapped host memory: set to 1 when any sample was re-routed
     unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far, core-precise} evaluations
 };
 

@@ -234,6 +234,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (tid == 0) {
                 const unsigned int slot = atomicAdd(Bt.fallback_count, 1u);
                 Bt.fallback_list[slot] = (int)b;
+                if (Bt.fallback_flag) *Bt.fallback_flag = 1;
             }
             continue;
         }
