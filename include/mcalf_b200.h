@@ -122,7 +122,7 @@ int mcalf_reset_stats(mcalf_ctx *ctx);
  *                      (default 0 = never: the reference never skips);
  *          "far_eps"   optical-depth error allowed to a (line, chunk) pair that is folded into the
  *                      chunk's far-field expansion of the Lorentzian wings (default 1e-9; 0 = never);
- *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default and
+ *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default 0.01,
  *                      upper limit 0.02: the validity range of the fp32 line-core series);
  *          "collect_stats" 0/1; "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);
  *          "ctas_per_sm" persistent CTAs per SM (0 = what the occupancy calculator allows);

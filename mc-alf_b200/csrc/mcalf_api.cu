@@ -41,7 +41,8 @@ constexpr size_t ZC_PARAM_BYTES = 256u << 10;  // zero-copy path: at most 256 KB
 constexpr long long ZC_MAX_ROWS = 1024;       // ... and 1024 rows
 constexpr double FWHM_TO_SIGMA_H = 2.354820;   // hires_fitter.py:454
 constexpr double TRUNC_SIGMAS_H = 3.0348;      // hires_fitter.py:458
-constexpr double A_MAX_LIMIT = 0.02;
+constexpr double A_MAX_LIMIT = 0.02;      // beyond this the a^4 term of the core series is > 1e-6
+constexpr double A_MAX_DEFAULT = 0.01;    // default hand-over to the fp64 kernel: fp32 forms good to 3e-7 below it
 constexpr int FF_NC_HOST = 8;          // far-field coefficients per chunk (FF_DEG + 1 in voigt_math.cuh)
 
 struct Slot {
@@ -459,7 +460,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     P.velstep = p->velstep;
     P.asym_t5 = p->asym_thresh5;
     P.asym_t4 = p->asym_thresh4;
-    P.a_max = A_MAX_LIMIT;
+    P.a_max = A_MAX_DEFAULT;
     P.eps_cull = 0.0f;
     P.eps_far = 1e-9f;
     P.Lmax = std::max(p->ncompmax * p->nlines + p->nfill, std::max(p->nlines, 1));
