@@ -197,6 +197,9 @@ def run_ours(args):
         if world == 1 and args.gpus > 1:
             sys.exit("bench.py --gpus %d must be launched with torchrun (one rank per GPU)" % args.gpus)
         args.gpus = world
+    # the CPU-baseline workers are forked before CUDA is initialised in this process (fork after CUDA
+    # initialisation is unsafe); they sleep until the GPU measurements are done
+    cpu_workers = cpu_pool() if (rank == 0 and world == 1 and not args.no_cpu) else None
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -324,8 +327,8 @@ def run_ours(args):
         }
         # ---- CPU baseline: oracle port on the host cores, bounded sample of the same vectors ----
         cpu = None
-        if world == 1 and not args.no_cpu:
-            pool, cores = cpu_pool()
+        if cpu_workers is not None:
+            pool, cores = cpu_workers
             ncpu = max(cores * 32, 512)          # ~20 s of CPU work in total
             tcpu = cpu_time(pool, cores, Uh[:ncpu])
             pool.close()

@@ -96,7 +96,8 @@ void mcalf_destroy(mcalf_ctx *ctx);
  * logL for B parameter vectors (row b at params + b*ld): replaces lnlhood_worker (:287-328) =
  * reconstruct_spec (:409-449) -> voigt_model/voigt_tau (:331-377) -> convolve_model (:452-464) ->
  * -0.5*nansum(...).  chi2_out may be NULL (else: chi2(p), :236-248).  stream: cudaStream_t or NULL.
- * With host pointers the call stages through pinned memory and returns after the results landed;
+ * With host pointers the call returns after the results landed (small calls go through mapped pinned
+ * memory, large ones through a copy-stream / compute-stream pipeline over pinned staging slices);
  * with MCALF_F_ON_DEVICE it only enqueues work on `stream`.
  */
 int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
