@@ -56,8 +56,8 @@ CANON_CORE, CANON_WING = 242.0, 36.0
 
 
 def cfg4_spectrum():
-    from oracle import mcalf_oracle as orc   # inputs only (shared by tests and bench); not the measured path
-    return orc.config_kwargs(4, GOLDEN)
+    from mcalf_b200.workloads import config_kwargs    # input generation only
+    return config_kwargs(4, GOLDEN)
 
 
 def make_fitter(device):

@@ -3,12 +3,12 @@ import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import mcalf_b200
-from oracle import mcalf_oracle as orc
+from mcalf_b200.workloads import config_kwargs
 
 GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
 def make(cfg):
-    spec, kw = orc.config_kwargs(cfg, GOLD)
+    spec, kw = config_kwargs(cfg, GOLD)
     return mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
         **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items() if k not in ("fitrange", "fitlines", "ncomp")})
 
