@@ -305,11 +305,13 @@ def run_ours(args):
             sm_max = 1965.0
         peak_nominal = geo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
         achieved = flop / (kernel_ms * 1e-3) / 1e12
-        traffic = None
+        traffic, ncu = None, None
         try:   # dram__bytes_read + dram__bytes_write of this kernel at this batch size, from the committed ncu capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if tr.get("batch") == B:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+            ncu = {k: tr[k] for k in ("issue_active_pct", "pipe_fma_pct", "pipe_alu_pct", "pipe_xu_pct", "pipe_lsu_pct",
+                                      "warp_instructions_per_logL", "source") if k in tr}
         except (OSError, ValueError, KeyError):
             pass
         roofline = {
@@ -324,6 +326,7 @@ def run_ours(args):
             "canonical_flop_per_logL": canon / B, "canonical_tflops": canon / (kernel_ms * 1e-3) / 1e12,
             "canonical_frac_of_nominal": canon / (kernel_ms * 1e-3) / 1e12 / peak_nominal,
             "hbm_bytes_per_logL": g.ndim * 8 + 8,
+            "ncu": ncu,     # from the committed capture under profiles/ (not measured in this run)
         }
         # ---- CPU baseline: oracle port on the host cores, bounded sample of the same vectors ----
         cpu = None
