@@ -64,3 +64,26 @@ def test_pool_falls_back_for_foreign_functions():
     other = FakeFitter()
     pool.map(other.lnlhood_dy, [np.zeros(3)])            # another fitter's method: not batched through ours
     assert f.batches == [] and other.batches == [1]
+
+
+def test_batched_nested_sampler_on_a_gaussian():
+    """The built-in batched sampler against a likelihood with a known evidence (CPU, fake fitter)."""
+    from mcalf_b200.nested import batched_nested_sampling, equal_weight_resample
+
+    class Gauss:
+        ndim, startind = 3, 0          # dimension 0 plays the (ignored) integer slot
+        mu, sig = np.array([0.5, 0.4, 0.6]), 0.05
+
+        def lnlhood_batch(self, U, unit_cube=False):
+            d = (np.asarray(U)[:, 1:] - self.mu[1:]) / self.sig
+            return -0.5 * np.sum(d * d, axis=1)
+
+        def prior_transform_batch(self, U):
+            return np.asarray(U)
+
+    r = batched_nested_sampling(Gauss(), nlive=300, batch=1024, seed=3)
+    expect = 2 * np.log(0.05 * np.sqrt(2 * np.pi))          # two Gaussian dimensions well inside the unit cube
+    assert abs(r["logz"] - expect) < 0.25, (r["logz"], expect)
+    s, _ = equal_weight_resample(r, 2000)
+    assert np.allclose(s[:, 1:].mean(axis=0), [0.4, 0.6], atol=0.01)
+    assert r["nlaunch"] * 1024 + 300 >= r["ncall"]
