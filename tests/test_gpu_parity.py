@@ -390,3 +390,21 @@ def test_batched_nested_sampling_recovers_the_mock_truth(tmp_path):
     assert np.allclose(stored, again, rtol=1e-12)
     print("nested sampling: %d likelihood calls in %d launches, %.2f s, logZ %.2f +/- %.2f, median %s"
           % (r["ncall"], r["nlaunch"], dt, r["logz"], r["logz_err"], med))
+
+
+@pytest.mark.parametrize("a0", [1e-5, 1e-4, 1e-3, 1e-2])
+def test_device_faddeeva_vs_wofz(a0):
+    """Re w(u + i a) as the kernels compute it (mcalf_voigt_h) against scipy.special.wofz -- the
+    reference's own Faddeeva (hires_fitter.py:365): fp32 forms to 5e-7 relative, fp64 form to 1e-12."""
+    from scipy.special import wofz
+    from mcalf_b200 import capi
+    rng = np.random.default_rng(5)
+    u = np.concatenate([rng.uniform(-12, 12, 200000), rng.uniform(-3000, 3000, 50000)]).astype(np.float32).astype(float)
+    a = np.full_like(u, np.float32(a0))
+    ref = wofz(u + 1j * a).real
+    got32 = capi.voigt_h(u, a, mode=0)
+    assert (np.abs(got32 - ref) / ref).max() < 5e-7
+    got64 = capi.voigt_h(u, a, mode=1)
+    assert (np.abs(got64 - ref) / ref).max() < 1e-12
+    big = capi.voigt_h(rng.uniform(-30, 30, 20000), np.full(20000, 2.5), mode=1)      # large damping: fp64 only
+    assert np.isfinite(big).all()
