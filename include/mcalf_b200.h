@@ -113,8 +113,9 @@ int mcalf_model_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t l
 int mcalf_prior_transform_batch(mcalf_ctx *ctx, const double *cube, int64_t B, int64_t ld, uint32_t flags,
                                 void *stream, double *theta_out);
 
-/* Re w(u + i a) element-wise with the kernels' own device code (fp32 fast path: mode 0,
- * fp64 check path: mode 1); for unit tests against scipy.special.wofz (:365). Host pointers. */
+/* Re w(u + i a) element-wise with the kernels' own device code (mode 0: fp32 wing / two-float core
+ * forms, mode 2: fp32 wing / short core form of weak lines, mode 1: fp64 check path); for unit tests
+ * against scipy.special.wofz (:365). Host pointers. */
 int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_t n, double *h_out);
 
 int mcalf_get_stats(mcalf_ctx *ctx, mcalf_stats_t *out);

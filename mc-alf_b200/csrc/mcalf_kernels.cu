@@ -650,7 +650,13 @@ __global__ void mcalf_prior_kernel(const __grid_constant__ DevProblem P, const d
 // element-wise Re w(u + i a) with the kernels' own device functions (unit tests)
 __global__ void mcalf_voigt_h_kernel(int mode, const double *u, const double *a, long long n, double *out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        out[i] = mode ? voigt_h64(a[i], u[i]) : (double)voigt_h32((float)a[i], (float)u[i]);
+    {
+        if (mode == 1) { out[i] = voigt_h64(a[i], u[i]); continue; }
+        const float af = (float)a[i], uf = (float)u[i];
+        // mode 0: wing form / two-float core form; mode 2: wing form / the short core form of weak lines
+        if (mode == 2 && fma32(uf, uf, af * af) < S_CUT) out[i] = (double)core_h32_lean(af, af * af, uf);
+        else out[i] = (double)voigt_h32(af, uf);
+    }
 }
 
 // FFMA-only loop: the measured FP32 peak the roofline fraction is also quoted against

@@ -408,3 +408,20 @@ def test_device_faddeeva_vs_wofz(a0):
     assert (np.abs(got64 - ref) / ref).max() < 1e-12
     big = capi.voigt_h(rng.uniform(-30, 30, 20000), np.full(20000, 2.5), mode=1)      # large damping: fp64 only
     assert np.isfinite(big).all()
+
+
+@pytest.mark.parametrize("a0", [1e-5, 1e-4, 1e-3, 1e-2])
+def test_device_faddeeva_short_core_form(a0):
+    """The short line-core form used for weak lines (kappa <= 8; one-float u, MUFU.EX2): absolute error
+    below 2.5e-7 and relative error below 2e-6 everywhere inside the core, which bounds the flux error
+    F * kappa * dH by 0.37 * 2.5e-7 (the sensitivity F * tau peaks at tau = 1)."""
+    from scipy.special import wofz
+    from mcalf_b200 import capi
+    u = np.random.default_rng(6).uniform(-6, 6, 300000).astype(np.float32).astype(float)
+    a = np.full_like(u, np.float32(a0))
+    ref = wofz(u + 1j * a).real
+    got = capi.voigt_h(u, a, mode=2)
+    assert np.abs(got - ref).max() < 2.5e-7
+    assert (np.abs(got - ref) / ref).max() < 2e-6
+    kappa = 8.0
+    assert (kappa * np.exp(-kappa * ref) * np.abs(got - ref)).max() < 1e-7
