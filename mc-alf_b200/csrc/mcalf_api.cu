@@ -296,7 +296,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
 
     // Large logL / chi2 calls: one copy stream feeds a ring of device slices, one compute stream runs the
     // kernels back to back; only the first slice's H2D is exposed, and the results come back in one copy.
-    if (!flux && B > c->slice) {
+    if (!flux && B > std::min<long long>(c->slice, 8192)) {
         const long long slice = c->slice;
         const bool pin_in = is_pinned(params), pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2);
         if (!c->copy_stream) {
@@ -310,7 +310,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
             CU(cudaMalloc((void **)&c->pipe_dout, obytes));
             c->pipe_dout_cap = obytes;
         }
-        if ((!pin_logl || (chi2 && !pin_chi2)) && obytes > c->pipe_hout_cap) {
+        if (((logl && !pin_logl) || (chi2 && !pin_chi2)) && obytes > c->pipe_hout_cap) {
             if (c->pipe_hout) CU(cudaFreeHost(c->pipe_hout));
             CU(cudaMallocHost((void **)&c->pipe_hout, obytes));
             c->pipe_hout_cap = obytes;
