@@ -296,7 +296,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
 
     // Large logL / chi2 calls: one copy stream feeds a ring of device slices, one compute stream runs the
     // kernels back to back; only the first slice's H2D is exposed, and the results come back in one copy.
-    if (!flux && B > std::min<long long>(c->slice, 8192)) {
+    if (!flux && B > std::min<long long>(c->slice, 2048)) {
         const long long slice = c->slice;
         const bool pin_in = is_pinned(params), pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2);
         if (!c->copy_stream) {
@@ -318,8 +318,8 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         double *d_logl = c->pipe_dout, *d_chi2 = c->pipe_dout + B;
         long long k = 0, n = 0;
         for (long long off = 0; off < B; off += n, ++k) {
-            // ramp the first slices up (4096, 8192, ...): only the first H2D is exposed, so keep it short
-            n = std::min(std::min(slice, (long long)4096 << std::min<long long>(k, 8)), B - off);
+            // ramp the first slices up (1024, 2048, ...): only the first staging copy + H2D is exposed, so keep it short
+            n = std::min(std::min(slice, (long long)1024 << std::min<long long>(k, 10)), B - off);
             const int r = (int)(k % NRING);
             Slot &s = c->ring[r];
             int rc = ensure_slot(c, s, slice, ld, 0, true);
