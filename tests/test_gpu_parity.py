@@ -94,6 +94,9 @@ def test_prior_draws_vs_oracle(cfg, B):
     P = np.array([o._scale_cube_pc(u) for u in U])
     assert np.array_equal(g.prior_transform_batch(U), P)            # bit-exact prior transform
     assert np.array_equal(np.array([g._scale_cube_pc(u) for u in U]), P)
+    Pmn = np.array([o._scale_cube_mn(u.copy()) for u in U])          # MultiNest form: no int() on the ncomp slot
+    assert np.array_equal(g.prior_transform_batch(U, no_trunc=True), Pmn)
+    assert np.array_equal(g.lnlhood_batch(U[:16], unit_cube=True, no_trunc=True), g.lnlhood_batch(Pmn[:16]))
     ref = np.array([o.lnlhood_worker(p) for p in P])
     got = g.lnlhood_batch(U, unit_cube=True)
     assert np.array_equal(got, g.lnlhood_batch(P))                  # same kernel either way
