@@ -302,11 +302,15 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             const int NS = P.nslots;
             const float *fslice = P.scratch_in_flux ? S.flux + P.halo + cd.start + (c & 31) : S.farp + (size_t)c * (FF_NC * NS + 1);
             const float *uslice = P.scratch_in_flux ? fslice + (FF_NC * NS + 1) : S.uarr + (size_t)c * P.Lmax;
-            float d[PX], tau[PX];
+            // rows (32 consecutive pixels) are held in pairs: {row 2j, row 2j+1} in one 64-bit register pair,
+            // so the arithmetic below runs on the packed FFMA2 / FMUL2 forms
+            constexpr int PX2 = PX / 2;
+            F2 d[PX2], tau[PX2];
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const int k = j * 32 + lane;
-                d[j] = (k < cd.len) ? __ldg(P.delta_hi + cd.start + k) : 0.0f;
+            for (int j = 0; j < PX2; ++j) {
+                const int k = 2 * j * 32 + lane;
+                d[j].x = (k < cd.len) ? __ldg(P.delta_hi + cd.start + k) : 0.0f;
+                d[j].y = (k + 32 < cd.len) ? __ldg(P.delta_hi + cd.start + k + 32) : 0.0f;
             }
             // far lines: sum the slots' partial expansions in slot order (lane n sums coefficient n),
             // broadcast, one polynomial per pixel
@@ -317,8 +321,18 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 float C[FF_NC];
 #pragma unroll
                 for (int n = 0; n < FF_NC; ++n) C[n] = __shfl_sync(0xffffffffu, cn, n);
+                F2 x[PX2];
 #pragma unroll
-                for (int j = 0; j < PX; ++j) tau[j] = farfield_eval(C, d[j] * cd.inv_ds);
+                for (int j = 0; j < PX2; ++j) {
+                    x[j] = mul2(d[j], f2(cd.inv_ds));
+                    tau[j] = f2(C[FF_DEG]);
+                }
+#pragma unroll
+                for (int n = FF_DEG - 1; n >= 0; --n) {
+                    const F2 cn2 = f2(C[n]);
+#pragma unroll
+                    for (int j = 0; j < PX2; ++j) tau[j] = fma2(tau[j], x[j], cn2);
+                }
             }
             // near lines, direct wing form, in line order: 8 evaluations per lane per line; inside a line
             // core the clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
@@ -329,12 +343,14 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
                     const int t = (w << 5) + __ffs(m) - 1;
                     const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
-                    const float Uh = uslice[t];
+                    const F2 A2 = f2(L.x), U2 = f2(uslice[t]), a22 = f2(L.y), c12 = f2(L.z);
 #pragma unroll
-                    for (int j = 0; j < PX; ++j) {
-                        const float u = fma32(L.x, d[j], Uh);
-                        const float s = fmaxf(fma32(u, u, L.y), S_CUT);
-                        tau[j] += wing_tau(L.z, s);
+                    for (int j = 0; j < PX2; ++j) {
+                        const F2 u = fma2(A2, d[j], U2);
+                        F2 s2 = fma2(u, u, a22);
+                        s2.x = fmaxf(s2.x, S_CUT);
+                        s2.y = fmaxf(s2.y, S_CUT);
+                        tau[j] = add2(tau[j], wing_tau2(c12, s2));
                     }
                 }
             }
@@ -344,8 +360,11 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (anycore) {
                 float *tcore = S.flux + P.halo + cd.start;
 #pragma unroll
-                for (int j = 0; j < PX; ++j)
-                    if (j * 32 + lane < cd.len) tcore[j * 32 + lane] = tau[j];
+                for (int j = 0; j < PX2; ++j) {
+                    const int k = 2 * j * 32 + lane;
+                    if (k < cd.len) tcore[k] = tau[j].x;
+                    if (k + 32 < cd.len) tcore[k + 32] = tau[j].y;
+                }
                 __syncwarp();
                 for (int w = 0; w < MW; ++w) {
                     unsigned cm = S.cmask[c * MW + w];
@@ -404,13 +423,17 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 }
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < PX; ++j)
-                    if (j * 32 + lane < cd.len) tau[j] = tcore[j * 32 + lane];
+                for (int j = 0; j < PX2; ++j) {
+                    const int k = 2 * j * 32 + lane;
+                    if (k < cd.len) tau[j].x = tcore[k];
+                    if (k + 32 < cd.len) tau[j].y = tcore[k + 32];
+                }
             }
 #pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                const int k = j * 32 + lane;
-                if (k < cd.len) S.flux[P.halo + cd.start + k] = depth32(tau[j]);
+            for (int j = 0; j < PX2; ++j) {
+                const int k = 2 * j * 32 + lane;
+                if (k < cd.len) S.flux[P.halo + cd.start + k] = depth32(tau[j].x);
+                if (k + 32 < cd.len) S.flux[P.halo + cd.start + k + 32] = depth32(tau[j].y);
             }
             __syncwarp();
         }

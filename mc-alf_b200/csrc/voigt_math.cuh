@@ -52,6 +52,35 @@ MCALF_HD float fma32(float a, float b, float c) {
 #endif
 }
 
+// Packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: fma|mul|add.rn.f32x2, sm_100+).  One instruction
+// does two IEEE-rounded fp32 operations -- the same bits as two scalar operations -- at half the warp
+// issue rate, which is what an issue-bound kernel needs: the FP work occupies half the issue slots.
+struct alignas(8) F2 { float x, y; };
+MCALF_HD F2 f2(float a, float b) { F2 r; r.x = a; r.y = b; return r; }
+MCALF_HD F2 f2(float a) { F2 r; r.x = a; r.y = a; return r; }
+#if defined(__CUDA_ARCH__)
+#define MCALF_PK(v) (*reinterpret_cast<const unsigned long long *>(&(v)))
+MCALF_HD F2 fma2(F2 a, F2 b, F2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(MCALF_PK(a)), "l"(MCALF_PK(b)), "l"(MCALF_PK(c)));
+    return *reinterpret_cast<F2 *>(&d);
+}
+MCALF_HD F2 mul2(F2 a, F2 b) {
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(MCALF_PK(a)), "l"(MCALF_PK(b)));
+    return *reinterpret_cast<F2 *>(&d);
+}
+MCALF_HD F2 add2(F2 a, F2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(MCALF_PK(a)), "l"(MCALF_PK(b)));
+    return *reinterpret_cast<F2 *>(&d);
+}
+#else
+MCALF_HD F2 fma2(F2 a, F2 b, F2 c) { return f2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+MCALF_HD F2 mul2(F2 a, F2 b) { return f2(a.x * b.x, a.y * b.y); }
+MCALF_HD F2 add2(F2 a, F2 b) { return f2(a.x + b.x, a.y + b.y); }
+#endif
+
 MCALF_HD float rcp32(float x) {
 #if defined(__CUDA_ARCH__)
     float r;
@@ -375,6 +404,17 @@ MCALF_HD LineP line_pack_full(const Line64 &L) {
     LineP o = line_pack(L);
     o.c1w = wing_tau(o.c1, S_CUT);
     return o;
+}
+
+// the wing form on a pair of pixels; s2 already clamped where needed
+MCALF_HD F2 wing_tau2(F2 c1, F2 s) {
+    const float w[5] = MCALF_WING_P;
+    const F2 q = f2(rcp32(s.x), rcp32(s.y));
+    F2 p = fma2(f2(w[4]), q, f2(w[3]));
+    p = fma2(p, q, f2(w[2]));
+    p = fma2(p, q, f2(w[1]));
+    p = fma2(p, q, f2(w[0]));
+    return mul2(mul2(c1, q), p);
 }
 
 // two-float u = A*delta + U for the line core
