@@ -537,7 +537,13 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
 #define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) return rc;
     std::vector<float2> d2(npix + 64, make_float2(0.f, 0.f));      // padded: the core pass reads 32 ahead unguarded
     for (int i = 0; i < npix; ++i) d2[i] = make_float2(dhi[i], dlo[i]);
-    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
+    std::vector<float4> d4(npix + 64, make_float4(0.f, 0.f, 0.f, 0.f));
+    for (const ChunkDesc &cd : chunks)
+        for (int i = cd.start; i < cd.start + cd.len; ++i) {
+            const bool pair = i + 32 < cd.start + cd.len;
+            d4[i] = make_float4(dhi[i], pair ? dhi[i + 32] : 0.f, dlo[i], pair ? dlo[i + 32] : 0.f);
+        }
+    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UP(d4, delta4) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
     UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)
 #undef UP
 #undef UPF4

@@ -23,7 +23,9 @@ struct DevProblem {
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
     const float *delta_hi, *delta_lo;   // [npix] rho_i - rho_s(chunk) as a two-float
-    const float2 *delta2;               // [npix] the same, interleaved {hi, lo} (line-core pass)
+    const float2 *delta2;               // [npix] the same, interleaved {hi, lo} (line-core pass, strong lines)
+    const float4 *delta4;               // [npix + 64] {hi[k], hi[k+32], lo[k], lo[k+32]}: pixel pairs of the packed core pass
+                                        // (zero where k+32 leaves the chunk)
     const float4 *obj_hi4, *obj_lo4, *w4; // [npix4/4] flux as a two-float and weight 1/err^2, four pixels per element;
                                         // obj = w = 0 on dropped pixels and on the padding
     const ChunkDesc *chunks;            // [nchunks]

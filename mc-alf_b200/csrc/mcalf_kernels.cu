@@ -388,21 +388,24 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                             // branch-free, 64 consecutive pixels per trip (two per lane in flight): the
                             // loop is latency bound otherwise
                             // (the delta table is padded by 64 entries, so the second load needs no bounds test)
-                            const float2 *pa = dd + k_lo + lane;
+                            // delta4[k] = {hi[k], hi[k+32], lo[k], lo[k+32]}: the pair arrives packed
+                            const float4 *pa = P.delta4 + cd.start + k_lo + lane;
                             float *ta_p = tcore + k_lo + lane;
+                            const F2 A2 = f2(L.A_hi), Al2 = f2(L.A_lo), Uh2 = f2(Uh), Ul2 = f2(Ul);
 #pragma unroll 1
                             for (int ka = k_lo + lane; ka <= k_hi; ka += 64, pa += 64, ta_p += 64) {
                                 const bool vb = ka + 32 <= k_hi;
-                                const float2 da = __ldg(pa), db = __ldg(pa + 32);
-                                const float ta = ta_p[0];
-                                const float tb = vb ? ta_p[32] : 0.0f;
-                                const float ua = fma32(L.A_hi, da.x, Uh), ub = fma32(L.A_hi, db.x, Uh);
-                                const bool ca = fma32(ua, ua, L.a2) < S_CUT, cb = vb && fma32(ub, ub, L.a2) < S_CUT;
-                                const float uca = ua + fma32(L.A_hi, da.y, fma32(L.A_lo, da.x, Ul));
-                                const float ucb = ub + fma32(L.A_hi, db.y, fma32(L.A_lo, db.x, Ul));
-                                const float ha = core_h32_lean(L.a, L.a2, uca, g1_smem), hb = core_h32_lean(L.a, L.a2, ucb, g1_smem);
-                                if (ca) ta_p[0] = ta + fma32(L.kappa, ha, -L.c1w);
-                                if (cb) ta_p[32] = tb + fma32(L.kappa, hb, -L.c1w);
+                                const float4 dv = __ldg(pa);
+                                const F2 dh = f2(dv.x, dv.y), dl = f2(dv.z, dv.w);
+                                const F2 tc = f2(ta_p[0], vb ? ta_p[32] : 0.0f);
+                                const F2 u = fma2(A2, dh, Uh2);
+                                const F2 s2 = fma2(u, u, f2(L.a2));
+                                const bool ca = s2.x < S_CUT, cb = vb && s2.y < S_CUT;
+                                const F2 uc = add2(u, fma2(A2, dl, fma2(Al2, dh, Ul2)));
+                                const F2 hh = core_h32_lean2(L.a, L.a2, uc, g1_smem);
+                                const F2 v = add2(tc, fma2(f2(L.kappa), hh, f2(-L.c1w)));
+                                if (ca) ta_p[0] = v.x;
+                                if (cb) ta_p[32] = v.y;
                                 if (STATS) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
                             }
                         } else {
@@ -432,8 +435,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < PX2; ++j) {
                 const int k = 2 * j * 32 + lane;
-                if (k < cd.len) S.flux[P.halo + cd.start + k] = depth32(tau[j].x);
-                if (k + 32 < cd.len) S.flux[P.halo + cd.start + k + 32] = depth32(tau[j].y);
+                const F2 dep = depth32_2(tau[j]);
+                if (k < cd.len) S.flux[P.halo + cd.start + k] = dep.x;
+                if (k + 32 < cd.len) S.flux[P.halo + cd.start + k + 32] = dep.y;
             }
             __syncwarp();
         }

@@ -143,6 +143,28 @@ MCALF_HD float depth32(float x) {
     return fma32(-sc.f, r * q, 1.0f - sc.f);
 }
 
+// depth32 on a pair of optical depths (packed where both lanes run the same operation)
+MCALF_HD F2 depth32_2(F2 x) {
+    const float c[8] = MCALF_EXPM_C;
+    x = f2(fminf(x.x, 88.0f), fminf(x.y, 88.0f));
+    const F2 t = mul2(x, f2(1.44269504088896341f));
+    const F2 n = f2(rintf(t.x), rintf(t.y));
+    F2 r = fma2(n, f2(-0.693145751953125f), x);
+    r = fma2(n, f2(-1.42860676533018702e-06f), r);
+    F2 q = fma2(f2(c[7]), r, f2(c[6]));
+    q = fma2(q, r, f2(c[5]));
+    q = fma2(q, r, f2(c[4]));
+    q = fma2(q, r, f2(c[3]));
+    q = fma2(q, r, f2(c[2]));
+    q = fma2(q, r, f2(c[1]));
+    union { int32_t i; float f; } sa, sb;
+    sa.i = (127 - (int)n.x) << 23;               // n in [0,127]
+    sb.i = (127 - (int)n.y) << 23;
+    const F2 sc = f2(sa.f, sb.f);
+    const F2 msc = f2(-sa.f, -sb.f);
+    return fma2(msc, mul2(r, q), add2(f2(1.0f), msc));
+}
+
 // tab: the table's copy in shared memory (kernels), or null for the global/host copy
 MCALF_HD G1Row g1_row(int j, const G1Row *tab = nullptr) {
 #if defined(__CUDA_ARCH__)
@@ -202,6 +224,28 @@ MCALF_HD float core_h32_lean(float a, float a2, float u, const G1Row *tab = null
     const float k1 = fma32(a2, fma32(-0.666666687f, x, 1.0f), 1.0f);
     const float inner = fma32(g1, k1, a2 * 0.376126389f);
     return fma32(g0, k0, a * inner);
+}
+
+// The short core form on a pair of pixels (same arithmetic as core_h32_lean, packed where the two lanes
+// of the pair run the same operation; the table look-ups, conversions and MUFU stay scalar).
+MCALF_HD F2 core_h32_lean2(float a, float a2, F2 u, const G1Row *tab = nullptr) {
+    const F2 x = mul2(u, u);
+    const F2 t = mul2(x, f2(-1.44269504088896341f));
+    const F2 g0 = f2(ex2_32(t.x), ex2_32(t.y));
+    const F2 au = f2(fabsf(u.x), fabsf(u.y));
+    const F2 fj = f2(rintf(au.x * (float)MCALF_G1_INV_H), rintf(au.y * (float)MCALF_G1_INV_H));
+    int ja = (int)fj.x, jb = (int)fj.y;
+    ja = ja < MCALF_G1_N - 1 ? ja : MCALF_G1_N - 1;
+    jb = jb < MCALF_G1_N - 1 ? jb : MCALF_G1_N - 1;
+    const F2 d = fma2(fj, f2(-1.0f / (float)MCALF_G1_INV_H), au);
+    const G1Row ta = g1_row(ja, tab), tb = g1_row(jb, tab);
+    const F2 g1 = f2(fma32(fma32(fma32(ta.c3, d.x, ta.c2), d.x, ta.c1), d.x, ta.c0),
+                     fma32(fma32(fma32(tb.c3, d.y, tb.c2), d.y, tb.c1), d.y, tb.c0));
+    const F2 a22 = f2(a2), one = f2(1.0f);
+    const F2 k0 = fma2(a22, fma2(f2(-2.0f), x, one), one);
+    const F2 k1 = fma2(a22, fma2(f2(-0.666666687f), x, one), one);
+    const F2 inner = fma2(g1, k1, f2(a2 * 0.376126389f));
+    return fma2(g0, k0, mul2(f2(a), inner));
 }
 
 // Convenience scalar form of the fast path (unit tests, mcalf_voigt_h): u, a as floats.
