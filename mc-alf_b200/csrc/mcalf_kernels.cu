@@ -258,9 +258,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const float ds = P.chunks[cs].ds;
                     float *fslice = P.scratch_in_flux ? S.flux + P.halo + P.chunks[cs].start + (cs & 31) : S.farp + (size_t)cs * fstride;   // skewed: lanes hit distinct banks
                     float *uslice = P.scratch_in_flux ? fslice + fstride : S.uarr + (size_t)cs * P.Lmax;
-                    float C[FF_NC];
+                    F2 C[FF_NC / 2];               // coefficient pairs {C[2m], C[2m+1]}
 #pragma unroll
-                    for (int n = 0; n < FF_NC; ++n) C[n] = 0.0f;
+                    for (int m = 0; m < FF_NC / 2; ++m) C[m] = f2(0.0f);
                     for (int t = slot; t < h.nact; t += NS) {
                         const double U = S.A64[t] * (rho_s - S.rc64[t]);
                         const float Uh = (float)U;
@@ -283,7 +283,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     }
                     if (cact) {
 #pragma unroll
-                        for (int n = 0; n < FF_NC; ++n) fslice[n * NS + slot] = C[n];
+                        for (int m = 0; m < FF_NC / 2; ++m) {
+                            fslice[(2 * m) * NS + slot] = C[m].x;
+                            fslice[(2 * m + 1) * NS + slot] = C[m].y;
+                        }
                     }
                 }
             }
@@ -485,14 +488,13 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // 2 w sum(resid) 1e-7 -- not small for one-signed residuals).  The pixel tables are padded
             // to a multiple of four with w = 0, so no pixel needs a bounds test here.
             const float4 oh = __ldg(P.obj_hi4 + g), ol = __ldg(P.obj_lo4 + g), ww = __ldg(P.w4 + g);
-            const float r0 = fma32(c_hi, o_0, (oh.x - c_hi) + (ol.x - c_lo)) + c_lo * o_0;
-            const float r1 = fma32(c_hi, o_1, (oh.y - c_hi) + (ol.y - c_lo)) + c_lo * o_1;
-            const float r2 = fma32(c_hi, o_2, (oh.z - c_hi) + (ol.z - c_lo)) + c_lo * o_2;
-            const float r3 = fma32(c_hi, o_3, (oh.w - c_hi) + (ol.w - c_lo)) + c_lo * o_3;
-            float part = (ww.x * r0) * r0;
-            part = fma32(ww.y * r1, r1, part);
-            part = fma32(ww.z * r2, r2, part);
-            part = fma32(ww.w * r3, r3, part);
+            const F2 mch = f2(-c_hi), mcl = f2(-c_lo), ch2 = f2(c_hi), cl2 = f2(c_lo);
+            const F2 oa = f2(o_0, o_1), ob = f2(o_2, o_3);
+            const F2 ra = add2(fma2(ch2, oa, add2(add2(f2(oh.x, oh.y), mch), add2(f2(ol.x, ol.y), mcl))), mul2(cl2, oa));
+            const F2 rb = add2(fma2(ch2, ob, add2(add2(f2(oh.z, oh.w), mch), add2(f2(ol.z, ol.w), mcl))), mul2(cl2, ob));
+            F2 p2 = mul2(mul2(f2(ww.x, ww.y), ra), ra);
+            p2 = fma2(mul2(f2(ww.z, ww.w), rb), rb, p2);
+            const float part = p2.x + p2.y;
             if (extras) {
                 const float out[4] = {o_0, o_1, o_2, o_3};
 #pragma unroll

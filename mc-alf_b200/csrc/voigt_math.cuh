@@ -405,8 +405,10 @@ MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float eps_c
     return 1;
 }
 
-// Add one far line's expansion coefficients (in x = delta/ds) to C[0..FF_DEG].
-MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, float a2, float *C) {
+// Add one far line's expansion coefficients (in x = delta/ds) to C[0..FF_DEG], held as pairs
+// {C[2m], C[2m+1]} (packed arithmetic: two coefficients per instruction).
+MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, float a2, F2 *C2) {
+    static_assert(FF_DEG % 2 == 1 && FF_DEG <= 9, "coefficient pairs; chunk_class computes r^(FF_DEG+1) by squaring; tables hold 10 binomials");
     const float iU = rcp32(U_hi);
     const float s = -(A_hi * ds) * iU;           // -r (signed)
     const float v = iU * iU;
@@ -416,13 +418,14 @@ MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, fl
     // binom(-2,n) = (-1)^n (n+1), binom(-4,n) = (-1)^n C(n+3,3), binom(-6,n) = (-1)^n C(n+5,5)
     const float b2[10] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f, 84.f, 120.f, 165.f, 220.f};
     const float b3[10] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f, 462.f, 792.f, 1287.f, 2002.f};
-    static_assert(FF_DEG % 2 == 1 && FF_DEG <= 9, "chunk_class computes r^(FF_DEG+1) by squaring; tables hold 10 binomials");
-    float sn = 1.0f;
+    const F2 T12 = f2(T1), T22 = f2(T2), T32 = f2(T3), ss = f2(s * s);
+    F2 sn = f2(1.0f, s);
 #pragma unroll
-    for (int n = 0; n <= FF_DEG; ++n) {
-        const float t = fma32((float)(n + 1), T1, fma32(b2[n], T2, b3[n] * T3));
-        C[n] = fma32(sn, t, C[n]);
-        sn *= s;
+    for (int m = 0; 2 * m <= FF_DEG; ++m) {
+        const int n = 2 * m;
+        const F2 t = fma2(f2((float)(n + 1), (float)(n + 2)), T12, fma2(f2(b2[n], b2[n + 1]), T22, mul2(f2(b3[n], b3[n + 1]), T32)));
+        C2[m] = fma2(sn, t, C2[m]);
+        sn = mul2(sn, ss);
     }
 }
 

@@ -51,7 +51,7 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
     for (size_t c = 0; c < chunks.size(); ++c) {
         const ChunkDesc &cd = chunks[c];
         // the kernel evaluates the far-field polynomial first, then the wing-only lines, then the mixed ones
-        float C[FF_DEG + 1] = {0};
+        F2 C2[(FF_DEG + 1) / 2] = {};
         int nf = 0;
         for (int pass = 0; pass <= 2; ++pass) {
             for (int t = 0; t < nlines; ++t) {
@@ -64,7 +64,7 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
                 const int cls = chunk_class(L.A_hi, Uh, cd.ds, L.c1, (float)eps_cull, (float)eps_far);
                 if (cls_out && pass == 0) cls_out[c * nlines + t] = cls;
                 if (pass == 0) {
-                    if (cls == 3) { farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C); ++nf; }
+                    if (cls == 3) { farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C2); ++nf; }
                     continue;
                 }
                 if (cls != pass) continue;
@@ -89,8 +89,11 @@ void emul_tau(long npix, const double *wave, int nlines, const double *lines, do
                     }
                 }
             }
-            if (pass == 0 && nf)
+            if (pass == 0 && nf) {
+                float C[FF_DEG + 1];
+                for (int m = 0; m < (FF_DEG + 1) / 2; ++m) { C[2 * m] = C2[m].x; C[2 * m + 1] = C2[m].y; }
                 for (int i = cd.start; i < cd.start + cd.len; ++i) tau[i] = farfield_eval(C, dhi[i] * cd.inv_ds);
+            }
         }
     }
     for (long i = 0; i < npix; ++i) tau_out[i] = (double)tau[i];
