@@ -81,6 +81,17 @@ MCALF_HD F2 mul2(F2 a, F2 b) { return f2(a.x * b.x, a.y * b.y); }
 MCALF_HD F2 add2(F2 a, F2 b) { return f2(a.x + b.x, a.y + b.y); }
 #endif
 
+// Round-to-nearest-integer of a * b (0 <= a*b < 2^22) without the conversion unit: adding 1.5 * 2^23
+// leaves the integer in the low mantissa bits.  n: the integer, return value: the same as a float.
+constexpr float RN_MAGIC = 12582912.0f;
+MCALF_HD float rn_mul(float a, float b, int &n) {
+    const float t = fma32(a, b, RN_MAGIC);
+    union { float f; int32_t i; } v;
+    v.f = t;
+    n = v.i - 0x4B400000;
+    return t - RN_MAGIC;
+}
+
 MCALF_HD float rcp32(float x) {
 #if defined(__CUDA_ARCH__)
     float r;
@@ -128,7 +139,8 @@ MCALF_HD float exp_neg32(float x, float xlo) {
 MCALF_HD float depth32(float x) {
     const float c[8] = MCALF_EXPM_C;
     x = fminf(x, 88.0f);
-    float n = rintf(x * 1.44269504088896341f);
+    int ni;
+    float n = rn_mul(x, 1.44269504088896341f, ni);
     float r = fma32(n, -0.693145751953125f, x);
     r = fma32(n, -1.42860676533018702e-06f, r);
     float q = fma32(c[7], r, c[6]);
@@ -137,9 +149,8 @@ MCALF_HD float depth32(float x) {
     q = fma32(q, r, c[3]);
     q = fma32(q, r, c[2]);
     q = fma32(q, r, c[1]);
-    int e = 127 - (int)n;               // n in [0,127]
     union { int32_t i; float f; } sc;
-    sc.i = e << 23;
+    sc.i = (127 - ni) << 23;            // n in [0,127]
     return fma32(-sc.f, r * q, 1.0f - sc.f);
 }
 
@@ -147,8 +158,8 @@ MCALF_HD float depth32(float x) {
 MCALF_HD F2 depth32_2(F2 x) {
     const float c[8] = MCALF_EXPM_C;
     x = f2(fminf(x.x, 88.0f), fminf(x.y, 88.0f));
-    const F2 t = mul2(x, f2(1.44269504088896341f));
-    const F2 n = f2(rintf(t.x), rintf(t.y));
+    const F2 tm = fma2(x, f2(1.44269504088896341f), f2(RN_MAGIC));      // rn_mul, packed
+    const F2 n = add2(tm, f2(-RN_MAGIC));
     F2 r = fma2(n, f2(-0.693145751953125f), x);
     r = fma2(n, f2(-1.42860676533018702e-06f), r);
     F2 q = fma2(f2(c[7]), r, f2(c[6]));
@@ -158,8 +169,11 @@ MCALF_HD F2 depth32_2(F2 x) {
     q = fma2(q, r, f2(c[2]));
     q = fma2(q, r, f2(c[1]));
     union { int32_t i; float f; } sa, sb;
-    sa.i = (127 - (int)n.x) << 23;               // n in [0,127]
-    sb.i = (127 - (int)n.y) << 23;
+    union { float f; int32_t i; } ta, tb;
+    ta.f = tm.x;
+    tb.f = tm.y;
+    sa.i = (127 - (ta.i - 0x4B400000)) << 23;    // n in [0,127]
+    sb.i = (127 - (tb.i - 0x4B400000)) << 23;
     const F2 sc = f2(sa.f, sb.f);
     const F2 msc = f2(-sa.f, -sb.f);
     return fma2(msc, mul2(r, q), add2(f2(1.0f), msc));
@@ -214,9 +228,8 @@ MCALF_HD float core_h32_lean(float a, float a2, float u, const G1Row *tab = null
     const float x = u * u;
     const float g0 = ex2_32(x * -1.44269504088896341f);
     const float au = fabsf(u);
-    const float fj = rintf(au * (float)MCALF_G1_INV_H);
-    int j = (int)fj;
-    j = j < MCALF_G1_N - 1 ? j : MCALF_G1_N - 1;
+    int j;
+    const float fj = rn_mul(fminf(au, 6.03f), (float)MCALF_G1_INV_H, j);     // (the table ends at u = 6.03)
     const float d = fma32(fj, -1.0f / (float)MCALF_G1_INV_H, au);
     const G1Row t = g1_row(j, tab);
     const float g1 = fma32(fma32(fma32(t.c3, d, t.c2), d, t.c1), d, t.c0);
@@ -233,10 +246,13 @@ MCALF_HD F2 core_h32_lean2(float a, float a2, F2 u, const G1Row *tab = nullptr) 
     const F2 t = mul2(x, f2(-1.44269504088896341f));
     const F2 g0 = f2(ex2_32(t.x), ex2_32(t.y));
     const F2 au = f2(fabsf(u.x), fabsf(u.y));
-    const F2 fj = f2(rintf(au.x * (float)MCALF_G1_INV_H), rintf(au.y * (float)MCALF_G1_INV_H));
-    int ja = (int)fj.x, jb = (int)fj.y;
-    ja = ja < MCALF_G1_N - 1 ? ja : MCALF_G1_N - 1;
-    jb = jb < MCALF_G1_N - 1 ? jb : MCALF_G1_N - 1;
+    const F2 ac = f2(fminf(au.x, 6.03f), fminf(au.y, 6.03f));                // (the table ends at u = 6.03)
+    const F2 tm = fma2(ac, f2((float)MCALF_G1_INV_H), f2(RN_MAGIC));         // rn_mul, packed
+    const F2 fj = add2(tm, f2(-RN_MAGIC));
+    union { float f; int32_t i; } ua, ub;
+    ua.f = tm.x;
+    ub.f = tm.y;
+    const int ja = ua.i - 0x4B400000, jb = ub.i - 0x4B400000;
     const F2 d = fma2(fj, f2(-1.0f / (float)MCALF_G1_INV_H), au);
     const G1Row ta = g1_row(ja, tab), tb = g1_row(jb, tab);
     const F2 g1 = f2(fma32(fma32(fma32(ta.c3, d.x, ta.c2), d.x, ta.c1), d.x, ta.c0),
