@@ -51,7 +51,7 @@ struct Slot {
     double *h_params = nullptr, *d_params = nullptr;   // pinned / device, slice * ld_cap doubles
     double *h_out = nullptr, *d_out = nullptr;         // 2 * slice doubles (logL, chi2)
     void *h_flux = nullptr, *d_flux = nullptr;
-    size_t flux_cap = 0, params_cap = 0, out_cap = 0;
+    size_t flux_cap = 0, params_cap = 0, hparams_cap = 0, out_cap = 0;
     unsigned int *counters = nullptr;                  // [2][2]: {work counter, fallback count} x launch parity
     int parity = 0;
     BatchArgs pending{};                               // the last deferred fix-up (zero-copy path)
@@ -138,7 +138,9 @@ int choose_launch(mcalf_ctx *c) {
     return MCALF_OK;
 }
 
-int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_bytes, bool host_io) {
+// stage_in / stage_out: pinned staging buffers are only needed when the caller's buffers are pageable
+int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_bytes, bool host_io, bool stage_in = true,
+                bool stage_out = true) {
     if (!s.stream) {
         CU(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
@@ -155,14 +157,17 @@ int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_by
     if (!host_io) return MCALF_OK;
     const size_t pbytes = sizeof(double) * (size_t)n * (size_t)ld;
     if (pbytes > s.params_cap) {
-        if (s.h_params) CU(cudaFreeHost(s.h_params));
         if (s.d_params) CU(cudaFree(s.d_params));
-        CU(cudaMallocHost((void **)&s.h_params, pbytes));
         CU(cudaMalloc((void **)&s.d_params, pbytes));
         s.params_cap = pbytes;
     }
+    if (stage_in && pbytes > s.hparams_cap) {
+        if (s.h_params) CU(cudaFreeHost(s.h_params));
+        CU(cudaMallocHost((void **)&s.h_params, pbytes));
+        s.hparams_cap = pbytes;
+    }
     const size_t obytes = sizeof(double) * 2 * (size_t)n;
-    if (obytes > s.out_cap) {
+    if (stage_out && obytes > s.out_cap) {
         if (s.h_out) CU(cudaFreeHost(s.h_out));
         if (s.d_out) CU(cudaFree(s.d_out));
         CU(cudaMallocHost((void **)&s.h_out, obytes));
@@ -322,7 +327,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
             n = std::min(std::min(slice, (long long)1024 << std::min<long long>(k, 10)), B - off);
             const int r = (int)(k % NRING);
             Slot &s = c->ring[r];
-            int rc = ensure_slot(c, s, slice, ld, 0, true);
+            int rc = ensure_slot(c, s, slice, ld, 0, true, !pin_in, false);
             if (rc) return rc;
             if (k >= NRING) CU(cudaEventSynchronize(s.done));          // the ring slot's previous slice has been consumed
             const double *src = params + off * ld;
