@@ -506,6 +506,58 @@ class als_fitter:
         return self.reconstruct_onecomp_batch(np.array([[specresolution, continuum, N, z, b]], dtype=np.float64),
                                               fill=True)[0]
 
+    # ------------------------------------------------------------------------------------------
+    # derived quantities (hires_fitter.py:467-505).  The reference's versions index the parameter
+    # vector without the ncomp slot (p[3*comp+startind], :482/:499 -- stale since that slot was
+    # introduced) and sum over ncompmax components; here the current layout is used (components at
+    # 1+3k+startind) and only the int(p[startind]) active components count.
+    # ------------------------------------------------------------------------------------------
+    def _single_line_fitter(self, lineid):
+        cache = self.__dict__.setdefault("_line_fitters", {})
+        if lineid not in cache:
+            lp = self.linepars[lineid]
+            name = "line%d" % lineid
+            cache[lineid] = als_fitter((self.obj_wl, self.obj, self.obj_noise), [[self.obj_wl.min() - 1.0, self.obj_wl.max() + 1.0]],
+                                       [name], [1, 1], specres=[0.0], contval=[1.0], device=self.device,
+                                       atomic={name: (lp["wrest"].value, lp["f"], lp["gamma"].value)})
+        return cache[lineid]
+
+    def calc_w_batch(self, P, lineid=0, max_rows=4096):
+        """Rest-frame equivalent width of line ``lineid`` summed over the active components, per row of
+        ``P`` (batched ``calc_w``, :467-491): sum_k sum_i (1 - T_k(lambda_i)) dlambda_i / (1 + z_k), with the
+        unconvolved single-line transmission from the CUDA model kernel."""
+        P = np.ascontiguousarray(np.atleast_2d(np.asarray(P, dtype=np.float64)))
+        f1 = self._single_line_fitter(lineid)
+        dl = np.diff(self.obj_wl)
+        dl = np.insert(dl, 0, dl[0])                                       # :486-487
+        s = self.startind
+        out = np.zeros(P.shape[0])
+        rows, owner, zs = [], [], []
+        for i, p in enumerate(P):
+            for k in range(min(max(int(p[s]), 0), self.ncompmax)):
+                N, z, b = p[1 + 3 * k + s:4 + 3 * k + s]
+                rows.append((0.0, 1.0, N, z, b))
+                owner.append(i)
+                zs.append(z)
+        rows, owner, zs = np.array(rows, dtype=np.float64).reshape(-1, 5), np.array(owner, dtype=int), np.array(zs)
+        for lo in range(0, len(rows), max_rows):
+            flux = f1.reconstruct_onecomp_batch(rows[lo:lo + max_rows])
+            w = ((1.0 - flux) * dl[None, :]).sum(axis=1) / (1.0 + zs[lo:lo + max_rows])
+            np.add.at(out, owner[lo:lo + max_rows], w)
+        return out
+
+    def calc_w(self, p, lineid=0):
+        return float(self.calc_w_batch(np.asarray(p, dtype=np.float64)[None, :], lineid)[0])
+
+    def calc_N(self, p):
+        """log10 of the summed column density of the active components (:493-505)."""
+        p = np.asarray(p, dtype=np.float64)
+        s = self.startind
+        n = min(max(int(p[s]), 0), self.ncompmax)
+        if n == 0:
+            return -np.inf
+        return float(np.log10(np.sum(10.0 ** p[1 + s:1 + s + 3 * n:3])))
+
     def get_jax_likelihood(self):                                        # :521-695
         """A jax-callable ``p[ndim] -> logL`` for jaxns (cli.py:237): the CUDA path behind
         ``jax.pure_callback``; under ``vmap`` the whole block of live points arrives as one batch."""

@@ -250,6 +250,24 @@ class OracleFitter:
                     return -np.inf
         return float(lhood)
 
+    # ---- derived quantities (hires_fitter.py:467-505), with the CURRENT parameter layout: the reference
+    # indexes p[3*comp+startind] (no ncomp slot, :482/:499) and loops to ncompmax; the restatement follows
+    # the layout reconstruct_spec uses (:431) and the active components only
+    def calc_w(self, p, lineid=0):
+        wrest, f, gamma = self.linepars[lineid]
+        dl = np.diff(self.obj_wl)
+        dl = np.insert(dl, 0, dl[0])
+        s, wtot = self.startind, 0.0
+        for k in range(int(p[s])):
+            logN, z, b = p[1 + 3 * k + s:4 + 3 * k + s]
+            t = self._transmission(logN, z, b, (wrest, f, gamma))
+            wtot += np.sum((1.0 - t) * dl) / (1.0 + z)
+        return float(wtot)
+
+    def calc_N(self, p):
+        s, n = self.startind, int(p[self.startind])
+        return float(np.log10(np.sum(10.0 ** np.asarray(p[1 + s:1 + s + 3 * n:3])))) if n else -np.inf
+
     def lnlhood_batch(self, P):
         return np.array([self.lnlhood_worker(p) for p in np.atleast_2d(P)])
 

@@ -428,3 +428,15 @@ def test_device_faddeeva_short_core_form(a0):
     assert (np.abs(got - ref) / ref).max() < 2e-6
     kappa = 8.0
     assert (kappa * np.exp(-kappa * ref) * np.abs(got - ref)).max() < 1.5e-7     # measured 1.2e-7; the bar is 1e-6
+
+
+def test_derived_quantities():
+    """Equivalent width and total column density against the oracle restatement."""
+    o, g = fitters("cfg2")
+    P = np.array([o._scale_cube_pc(u) for u in np.random.default_rng(31).random((12, o.ndim))])
+    for lineid in (0, 1):
+        ref = np.array([o.calc_w(p, lineid) for p in P])
+        got = g.calc_w_batch(P, lineid)
+        assert np.allclose(got, ref, rtol=2e-6, atol=1e-7), np.abs(got / ref - 1).max()
+    assert g.calc_w(P[0]) == pytest.approx(o.calc_w(P[0]), rel=2e-6)
+    assert g.calc_N(P[0]) == pytest.approx(o.calc_N(P[0]), rel=1e-14)
