@@ -98,11 +98,12 @@ __device__ __forceinline__ void line_source(const DevProblem &P, const SampleHea
 
 // Normalised LSF taps into smem as floats, laid out for the register-blocked stencil:
 // G[m] = g_{m-n4}, m = 0 .. 2 n4, zero where |m - n4| > n; zero padded to 2 n4 + 4.   One warp.
-__device__ __forceinline__ int build_taps(const DevProblem &P, double specres, float *G, int lane) {
+__device__ __forceinline__ int build_taps(const DevProblem &P, double specres, float *G, int lane, int &nhalf) {
     int n = 0;
     double sigma = 1.0;
     const bool conv = specres > P.velstep;                       // hires_fitter.py:445
     if (conv) lsf_geometry(specres, P.velstep, sigma, n);
+    nhalf = n;
     if (n > P.nmax || n < 0) return -1;                          // wider than the halo the host sized from the bounds
     const int n4 = (n + 3) & ~3;
     const double inv2s2 = conv ? 0.5 / (sigma * sigma) : 0.0;
@@ -225,8 +226,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         for (int i = tid; i < P.nchunks * P.mwords; i += nthreads) { S.nmask[i] = 0u; S.cmask[i] = 0u; }
         int n4 = 0;
         if (warp == nwarps - 1) {
-            n4 = build_taps(P, h.specres, S.taps, lane);
-            if (lane == 0) S.misc[2] = n4;
+            int nhalf = 0;
+            n4 = build_taps(P, h.specres, S.taps, lane, nhalf);
+            if (lane == 0) { S.misc[2] = n4; S.misc[6] = nhalf; }
         }
         bad = __syncthreads_or(bad);
         if (bad || S.misc[2] < 0 || !(h.specres == h.specres) || !(h.cont == h.cont)) {
@@ -465,7 +467,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         double acc = 0.0;
         int cnt5 = 0, cnt4 = 0;
         const int ngroups = P.npix4 >> 2;
-        const int nb = (n4 >> 1) + 1;
+        // taps G[m] are non-zero for m in [n4 - n, n4 + n]: blocks of four taps up to the one holding n4 + n
+        const int nb = ((n4 + S.misc[6]) >> 2) + 1;
         const bool extras = Bt.flux_out != nullptr || P.asymmlike;
         for (int g = tid; g < ngroups; g += nthreads) {
             const int o0 = g << 2;
