@@ -8,7 +8,9 @@
  *
  * Conventions: plain pointers and sizes only; every function returns 0 on success or a negative
  * MCALF_E_* code, with a thread-local message available from mcalf_last_error().  The caller owns
- * every in/out buffer.  A context is bound to one CUDA device and one in-flight call at a time.
+ * every in/out buffer.  A context is bound to one CUDA device and serves one call at a time: a second
+ * thread entering a batch call while one is in flight gets MCALF_E_INVALID ("context busy"); use one
+ * context per thread.  Every call leaves the calling thread's current CUDA device as it found it.
  * There is no CPU fallback: without a usable CUDA device mcalf_create() fails.
  */
 #ifndef MCALF_B200_H
@@ -20,7 +22,7 @@
 extern "C" {
 #endif
 
-#define MCALF_ABI_VERSION 1
+#define MCALF_ABI_VERSION 2
 
 /* error codes */
 #define MCALF_OK 0
@@ -38,6 +40,9 @@ extern "C" {
 #define MCALF_F_ONECOMP_FILL 0x20 /* as ONECOMP but with the filler line: reconstruct_onecomp_fill (:394-406)    */
 #define MCALF_F_NO_TRUNC 0x40   /* with UNIT_CUBE: _scale_cube_mn semantics, no int() on the ncomp slot (:211-216) */
 #define MCALF_F_FLUX_F64 0x80   /* mcalf_model_batch: flux_out is double[B*npix] instead of float[B*npix]        */
+#define MCALF_F_ONELINE 0x100   /* params rows are [specres, continuum, N, z, b, line]: ONE line of the line table
+                                   (index `line`, nlines = the filler) of one component -- the single-line
+                                   voigt_model the reference's calc_w integrates (:467-491)                      */
 
 /*
  * Everything als_fitter.__init__ (hires_fitter.py:32-200) leaves behind that the likelihood reads.
@@ -81,10 +86,11 @@ typedef struct mcalf_stats {
     uint64_t evals_total;      /* (line, pixel) Voigt evaluations the reference would perform           */
     uint64_t evals_wing;       /* ... in (line, chunk) pairs served by the wing-only form               */
     uint64_t evals_mixed;      /* ... in pairs that may contain line-core pixels                        */
-    uint64_t evals_core;       /* ... of the mixed ones that took the line-core branch                  */
+    uint64_t evals_core;       /* (line, pixel) evaluations executed with a line-core form (whole 64-pixel row pairs) */
     uint64_t evals_culled;     /* ... skipped under the proven tau < cull_eps bound                     */
     uint64_t evals_far;        /* ... in pairs folded into the chunk's far-field polynomial             */
     uint64_t evals_core_precise; /* ... of the core ones that took the two-float form (kappa > 8)          */
+    uint64_t evals_core_straddle; /* ... of the core ones in row pairs that also needed the wing form (per-pixel select) */
     double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events)            */
 } mcalf_stats_t;
 
@@ -98,7 +104,9 @@ void mcalf_destroy(mcalf_ctx *ctx);
  * -0.5*nansum(...).  chi2_out may be NULL (else: chi2(p), :236-248).  stream: cudaStream_t or NULL.
  * With host pointers the call returns after the results landed (small calls go through mapped pinned
  * memory, large ones through a copy-stream / compute-stream pipeline over pinned staging slices);
- * with MCALF_F_ON_DEVICE it only enqueues work on `stream`.
+ * with MCALF_F_ON_DEVICE it only enqueues work on `stream` (successive device calls of one context may use
+ * different streams: each is ordered after the previous one with an event, because they share the
+ * context's work counters).
  */
 int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
                         void *stream, double *logl_out, double *chi2_out);
@@ -114,7 +122,8 @@ int mcalf_prior_transform_batch(mcalf_ctx *ctx, const double *cube, int64_t B, i
                                 void *stream, double *theta_out);
 
 /* Re w(u + i a) element-wise with the kernels' own device code (mode 0: fp32 wing / two-float core
- * forms, mode 2: fp32 wing / short core form of weak lines, mode 1: fp64 check path); for unit tests
+ * forms, mode 2: fp32 wing / short core form of weak lines, mode 3: the weak-line forms with the core
+ * boundary at s = 16 and the wide-interval wing polynomial, mode 1: fp64 check path); for unit tests
  * against scipy.special.wofz (:365). Host pointers. */
 int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_t n, double *h_out);
 

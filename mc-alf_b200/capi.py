@@ -8,10 +8,10 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcalf_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, E_INVALID, E_CUDA, E_NODEVICE, E_RESOURCE = 0, -1, -2, -3, -4
 F_UNIT_CUBE, F_ON_DEVICE, F_FP64, F_TARGONLY = 0x01, 0x02, 0x04, 0x08
-F_ONECOMP, F_ONECOMP_FILL, F_NO_TRUNC, F_FLUX_F64 = 0x10, 0x20, 0x40, 0x80
+F_ONECOMP, F_ONECOMP_FILL, F_NO_TRUNC, F_FLUX_F64, F_ONELINE = 0x10, 0x20, 0x40, 0x80, 0x100
 
 _dp = ctypes.POINTER(ctypes.c_double)
 
@@ -39,7 +39,7 @@ class Stats(ctypes.Structure):
     """mcalf_stats_t"""
     _fields_ = [(n, ctypes.c_uint64) for n in
                 ("kernel_launches", "samples", "samples_fp64", "evals_total", "evals_wing", "evals_mixed",
-                 "evals_core", "evals_culled", "evals_far", "evals_core_precise")] + [("last_kernel_ms", ctypes.c_double)]
+                 "evals_core", "evals_culled", "evals_far", "evals_core_precise", "evals_core_straddle")] + [("last_kernel_ms", ctypes.c_double)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

@@ -3,10 +3,12 @@
   <root>.stats               one line  ``log(Z)   : <v>   +/-   <e>``           (writer cli.py:292-295)
   <root>_equal_weights.txt   rows ``[weight, -2*logL, theta...]`` via np.savetxt (writer cli.py:312-325)
 
-``read_chains`` follows ``pc_analyzer`` (hires_fitter.py:704-747), including the redshift sort of the
-components and the NaN fill above ``thisncomp``; ``logl_of_chain`` re-evaluates a chain's samples in
+``read_chains`` returns what ``pc_analyzer`` (hires_fitter.py:704-747) returns for the same files, including
+the redshift sort of the components and the NaN fill above the active count (vectorised over the samples); ``logl_of_chain`` re-evaluates a chain's samples in
 one batch through the CUDA path (what the plotting code does point by point, cli.py:414-418).
 """
+import re
+
 import numpy as np
 
 
@@ -22,33 +24,42 @@ def write_equal_weights(filesbasename, logl, samples):
     np.savetxt(filesbasename + "_equal_weights.txt", out)
 
 
-def read_chains(filesbasename, return_sorted=True):
-    """-> (lnz, lnz_err, lhoodsamples, samples) exactly as ``pc_analyzer`` returns them."""
+_STATS_LINE = re.compile(r"^log\(Z\)\s*:\s*(\S+)\s*\+/-\s*(\S+)")
+
+
+def read_stats(filesbasename):
+    """(log Z, its error) from ``<root>.stats``; the last ``log(Z)`` line wins, as in the reference reader."""
     lnz = lnz_err = None
-    with open(filesbasename + ".stats", "r") as f:
-        for line in f:
-            if line[:6] == 'log(Z)':
-                items = line.split()
-                lnz, lnz_err = float(items[2]), float(items[4])
-    allsamples = np.loadtxt(filesbasename + "_equal_weights.txt", ndmin=2)
-    lhoodsamples = -0.5 * allsamples[:, 1]
-    postsamples = allsamples[:, 2:]
+    with open(filesbasename + ".stats", "r") as fh:
+        for m in filter(None, map(_STATS_LINE.match, fh)):
+            lnz, lnz_err = float(m.group(1)), float(m.group(2))
+    return lnz, lnz_err
+
+
+def read_chains(filesbasename, return_sorted=True):
+    """-> (lnz, lnz_err, logL of every sample, samples): what ``pc_analyzer`` (hires_fitter.py:704-747) returns
+    for the same files.  With ``return_sorted`` every row's active components (the first ``int(ncomp)``
+    [N, z, b] triples after the ncomp column) are reordered by increasing redshift and everything behind them
+    is NaN.  The column of the ncomp slot follows from the row length alone: (ncols - 1) mod 3."""
+    lnz, lnz_err = read_stats(filesbasename)
+    table = np.loadtxt(filesbasename + "_equal_weights.txt", ndmin=2)
+    logl = -0.5 * table[:, 1]
+    theta = table[:, 2:]
     if not return_sorted:
-        return lnz, lnz_err, lhoodsamples, postsamples
-    postsorted = np.copy(postsamples)
-    ncols = postsorted.shape[1]
-    startind = (ncols - 1) % 3
-    for ii in range(postsamples.shape[0]):
-        thisncomp = int(postsamples[ii, startind])
-        thisendind = startind + 1 + 3 * thisncomp
-        postsamples[ii, thisendind:] = 99
-        postsorted[ii, thisendind:] = 99
-        zsort = np.argsort(postsamples[ii, startind + 2:startind + 1 + 3 * thisncomp:3])
-        for jj in range(len(zsort)):
-            postsorted[ii, 3 * jj + startind + 1:3 * jj + 3 + startind + 1] = \
-                postsamples[ii, 3 * zsort[jj] + np.array([0, 1, 2]) + startind + 1]
-        postsorted[postsorted == 99] = np.nan
-    return lnz, lnz_err, lhoodsamples, postsorted
+        return lnz, lnz_err, logl, theta
+    n, ncols = theta.shape
+    first = (ncols - 1) % 3 + 1                        # first component column; the ncomp slot sits before it
+    ntrip = (ncols - first) // 3
+    trip = theta[:, first:].reshape(n, ntrip, 3)
+    nact = np.clip(theta[:, first - 1].astype(np.int64), 0, ntrip)
+    slot = np.arange(ntrip)[None, :]
+    active = slot < nact[:, None]
+    order = np.argsort(np.where(active, trip[:, :, 1], np.inf), axis=1, kind="stable")    # active ones first, by z
+    trip = np.take_along_axis(trip, order[:, :, None], axis=1)
+    trip[~active] = np.nan                             # after the sort the first nact slots are the active ones
+    out = theta.copy()
+    out[:, first:] = trip.reshape(n, 3 * ntrip)
+    return lnz, lnz_err, logl, out
 
 
 def logl_of_chain(fitter, filesbasename):

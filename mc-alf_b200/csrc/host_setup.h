@@ -73,4 +73,18 @@ inline void build_chunks(const double *wave, int npix, double lam_ref, std::vect
     }
 }
 
+// Pair tables of the fp32 kernel: a lane holds the pixels k and k + 32 of a 64-pixel row pair in one
+// register pair, so the tables store {v[i], v[i + 32]} at i (zero where i + 32 leaves the chunk).  Padded
+// by a full chunk: the kernel loads all 256 slots of a chunk without bounds tests (slots beyond a short
+// chunk read the next chunk's entries or the zero padding; nothing computed from them is stored).
+struct PairF { float x, y; };
+inline void build_pair_table(const std::vector<ChunkDesc> &chunks, const std::vector<float> &v, std::vector<PairF> &out) {
+    out.assign(v.size() + CHUNK_PIXELS, PairF{0.0f, 0.0f});
+    for (const ChunkDesc &cd : chunks)
+        for (int i = cd.start; i < cd.start + cd.len; ++i) {
+            out[i].x = v[i];
+            out[i].y = (i + 32 < cd.start + cd.len) ? v[i + 32] : 0.0f;
+        }
+}
+
 }  // namespace mcalf

@@ -10,6 +10,8 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <vector>
 
 #include "mcalf_device.h"
@@ -34,6 +36,24 @@ int fail(int code, const char *fmt, ...) {
         cudaError_t e_ = (call);                                                                   \
         if (e_ != cudaSuccess) return fail(MCALF_E_CUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
+
+// Every entry point runs on the context's device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceGuard(int dev) {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = -1; }
+        if (cur != dev) {
+            err = cudaSetDevice(dev);
+            prev = cur;
+        }
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                                                  \
+    DeviceGuard guard_(dev);                                                                            \
+    if (guard_.err != cudaSuccess) return fail(MCALF_E_CUDA, "cudaSetDevice(%d): %s", dev, cudaGetErrorString(guard_.err))
 
 constexpr int NBUF = 2;
 constexpr int NRING = 3;
@@ -82,7 +102,29 @@ struct mcalf_ctx {
     int collect_stats = 0;
     uint64_t kernel_launches = 0, samples = 0, samples_fp64 = 0;
     int last_slot = -1, last_ring = -1;
+    // one call at a time per context: the slots' counters, staging buffers and events are not re-entrant
+    std::atomic_flag busy = ATOMIC_FLAG_INIT;
+    // MCALF_F_ON_DEVICE calls may arrive on different streams: each one is ordered after the previous
+    cudaStream_t dev_last_stream = nullptr;
+    bool dev_has_last = false;
+    cudaEvent_t dev_order = nullptr;
+    // staging of the small utility calls (prior transform from host pointers)
+    cudaStream_t util_stream = nullptr;
+    double *util_dev = nullptr;
+    size_t util_cap = 0;
 };
+
+namespace {
+struct BusyGuard {
+    mcalf_ctx *c;
+    bool mine;
+    explicit BusyGuard(mcalf_ctx *ctx) : c(ctx), mine(!ctx->busy.test_and_set(std::memory_order_acquire)) {}
+    ~BusyGuard() { if (mine) c->busy.clear(std::memory_order_release); }
+};
+}  // namespace
+#define ONE_CALL(ctx)                                                                                          \
+    BusyGuard busy_(ctx);                                                                                      \
+    if (!busy_.mine) return fail(MCALF_E_INVALID, "context busy: another call on this context is in flight (use one context per thread)")
 
 namespace {
 
@@ -105,7 +147,10 @@ int choose_launch(mcalf_ctx *c) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
     size_t smem = fast_smem_bytes(P, nwarps);
-    const size_t static_smem = 3200;   // the kernel's fixed-address H1 table
+    size_t static_smem = 0;            // the kernel's fixed-address H1 table
+    // (also raises every kernel's dynamic shared-memory limit to what the device allows: the attribute is
+    // held per function and device, not per context, so it is never set to one problem's size)
+    CU(configure_kernels((size_t)prop.sharedMemPerBlockOptin, &static_smem));
     while (smem + static_smem > (size_t)prop.sharedMemPerBlockOptin && nwarps > 1) {
         nwarps = (nwarps + 1) / 2;
         smem = fast_smem_bytes(P, nwarps);
@@ -119,7 +164,6 @@ int choose_launch(mcalf_ctx *c) {
                     (size_t)prop.sharedMemPerBlockOptin);
     c->threads = nwarps * 32;
     c->smem_fast = smem;
-    CU(configure_kernels(c->smem_fast, c->smem_fp64));
     int occ = 0, occ_dense = 0;
     CU(fast_occupancy(c->threads, c->smem_fast, 0, &occ));   // accounts for the kernel's static shared memory too
     if (c->threads <= 256 && c->dense_opt == 1) CU(fast_occupancy(c->threads, c->smem_fast, 1, &occ_dense));
@@ -147,7 +191,8 @@ int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_by
         CU(cudaEventCreate(&s.k0));
         CU(cudaEventCreate(&s.k1));
         CU(cudaMalloc((void **)&s.counters, 4 * sizeof(unsigned int)));
-        CU(cudaMemset(s.counters, 0, 4 * sizeof(unsigned int)));
+        CU(cudaMemsetAsync(s.counters, 0, 4 * sizeof(unsigned int), s.stream));
+        CU(cudaStreamSynchronize(s.stream));      // done before the first launch, whatever stream that is on
     }
     if ((size_t)n > s.fallback_cap) {
         if (s.fallback) CU(cudaFree(s.fallback));
@@ -254,12 +299,14 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     if (B == 0) return MCALF_OK;
     if (B > (1LL << 30)) return fail(MCALF_E_INVALID, "batch of %lld rows: split calls above 2^30 rows", B);
     if (!params) return fail(MCALF_E_INVALID, "null params");
-    const int need = (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) ? 5 : c->P.ndim;
+    const uint32_t row5 = MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL | MCALF_F_ONELINE;
+    const int need = (flags & MCALF_F_ONELINE) ? 6 : (flags & row5) ? 5 : c->P.ndim;
     if (ld < need) return fail(MCALF_E_INVALID, "ld (%lld) smaller than the row length (%d)", ld, need);
-    if ((flags & MCALF_F_ONECOMP) && (flags & MCALF_F_ONECOMP_FILL)) return fail(MCALF_E_INVALID, "ONECOMP and ONECOMP_FILL are exclusive");
-    if ((flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) && (flags & MCALF_F_UNIT_CUBE))
-        return fail(MCALF_E_INVALID, "ONECOMP rows are physical parameters, not unit-cube draws");
-    CU(cudaSetDevice(c->device));
+    if (((flags & row5) & ((flags & row5) - 1)) != 0) return fail(MCALF_E_INVALID, "ONECOMP, ONECOMP_FILL and ONELINE are exclusive");
+    if ((flags & row5) && (flags & MCALF_F_UNIT_CUBE))
+        return fail(MCALF_E_INVALID, "ONECOMP / ONELINE rows are physical parameters, not unit-cube draws");
+    ON_DEVICE(c->device);
+    ONE_CALL(c);
     const size_t esize = (flags & MCALF_F_FLUX_F64) ? 8 : 4;
 
     if (flags & MCALF_F_ON_DEVICE) {
@@ -268,7 +315,17 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         if (rc) return rc;
         c->last_slot = NBUF;             // = dev_slot
         c->last_ring = -1;
-        return enqueue(c, s, (cudaStream_t)stream, params, B, ld, flags, logl, chi2, flux);
+        // the slot's counter pairs are handed from launch to launch: a call on another stream than the
+        // previous one waits for it (same stream: stream order already does)
+        cudaStream_t st = (cudaStream_t)stream;
+        if (!c->dev_order) CU(cudaEventCreateWithFlags(&c->dev_order, cudaEventDisableTiming));
+        if (c->dev_has_last && c->dev_last_stream != st) {
+            CU(cudaEventRecord(c->dev_order, c->dev_last_stream));
+            CU(cudaStreamWaitEvent(st, c->dev_order, 0));
+        }
+        c->dev_last_stream = st;
+        c->dev_has_last = true;
+        return enqueue(c, s, st, params, B, ld, flags, logl, chi2, flux);
     }
 
     // Small calls (the scalar callbacks of a CPU sampler, one live set): the kernel reads the parameters
@@ -435,7 +492,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     if (e != cudaSuccess || ndev < 1)
         return fail(MCALF_E_NODEVICE, "no CUDA device (%s): this library never computes on the host", e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(MCALF_E_INVALID, "device %d out of range (%d devices)", device, ndev);
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
 
     mcalf_ctx *c = new mcalf_ctx();
     struct Guard {                      // every early error return below releases the half-built context
@@ -540,18 +597,16 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     int rc;
 #define UPF4(vec, field) { const float *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) return rc; P.field = reinterpret_cast<const float4 *>(tmp_); }
 #define UP(vec, field) if ((rc = upload(c, vec, &P.field)) != MCALF_OK) return rc;
-    std::vector<float2> d2(npix + 64, make_float2(0.f, 0.f));      // padded: the core pass reads 32 ahead unguarded
-    for (int i = 0; i < npix; ++i) d2[i] = make_float2(dhi[i], dlo[i]);
-    std::vector<float4> d4(npix + 64, make_float4(0.f, 0.f, 0.f, 0.f));
-    for (const ChunkDesc &cd : chunks)
-        for (int i = cd.start; i < cd.start + cd.len; ++i) {
-            const bool pair = i + 32 < cd.start + cd.len;
-            d4[i] = make_float4(dhi[i], pair ? dhi[i + 32] : 0.f, dlo[i], pair ? dlo[i + 32] : 0.f);
-        }
-    UP(dhi, delta_hi) UP(dlo, delta_lo) UP(d2, delta2) UP(d4, delta4) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
+    std::vector<PairF> ph, pl;
+    build_pair_table(chunks, dhi, ph);
+    build_pair_table(chunks, dlo, pl);
+    static_assert(sizeof(PairF) == sizeof(float2), "pair table layout");
+#define UPF2(vec, field) { const PairF *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) return rc; P.field = reinterpret_cast<const float2 *>(tmp_); }
+    UPF2(ph, dhi2) UPF2(pl, dlo2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
     UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)
 #undef UP
 #undef UPF4
+#undef UPF2
     e = cudaMalloc((void **)&c->d_stats, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long));
     if (e != cudaSuccess) return fail(MCALF_E_CUDA, "stats buffer: %s", cudaGetErrorString(e));
@@ -563,7 +618,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
 
 void mcalf_destroy(mcalf_ctx *c) {
     if (!c) return;
-    cudaSetDevice(c->device);
+    DeviceGuard guard_(c->device);
     for (Slot &s : c->slot) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         if (s.h_params) cudaFreeHost(s.h_params);
@@ -609,6 +664,9 @@ void mcalf_destroy(mcalf_ctx *c) {
     if (c->pipe_hout) cudaFreeHost(c->pipe_hout);
     for (void *d : c->allocs) cudaFree(d);
     if (c->d_stats) cudaFree(c->d_stats);
+    if (c->dev_order) cudaEventDestroy(c->dev_order);
+    if (c->util_dev) cudaFree(c->util_dev);
+    if (c->util_stream) cudaStreamDestroy(c->util_stream);
     delete c;
 }
 
@@ -631,21 +689,29 @@ int mcalf_prior_transform_batch(mcalf_ctx *c, const double *cube, int64_t B, int
     if (B == 0) return MCALF_OK;
     if (!cube || !theta_out) return fail(MCALF_E_INVALID, "null buffer");
     if (ld < c->P.ndim) return fail(MCALF_E_INVALID, "ld (%lld) smaller than ndim (%d)", (long long)ld, c->P.ndim);
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
+    ONE_CALL(c);
     if (flags & MCALF_F_ON_DEVICE) {
         CU(launch_prior(c->P, cube, B, ld, flags, theta_out, (cudaStream_t)stream));
         c->kernel_launches += 1;
         return MCALF_OK;
     }
-    double *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMalloc((void **)&d_in, sizeof(double) * (size_t)B * (size_t)ld));
-    cudaError_t e = cudaMalloc((void **)&d_out, sizeof(double) * (size_t)B * (size_t)c->P.ndim);
-    if (e == cudaSuccess) e = cudaMemcpy(d_in, cube, sizeof(double) * (size_t)B * (size_t)ld, cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = launch_prior(c->P, d_in, B, ld, flags, d_out, nullptr);
-    if (e == cudaSuccess) e = cudaMemcpy(theta_out, d_out, sizeof(double) * (size_t)B * (size_t)c->P.ndim, cudaMemcpyDeviceToHost);
-    cudaFree(d_in);
-    if (d_out) cudaFree(d_out);
-    if (e != cudaSuccess) return fail(MCALF_E_CUDA, "prior transform: %s", cudaGetErrorString(e));
+    // host pointers: one device staging buffer per context, grown on demand and kept
+    const size_t nin = (size_t)B * (size_t)ld, nout = (size_t)B * (size_t)c->P.ndim;
+    if (!c->util_stream) CU(cudaStreamCreateWithFlags(&c->util_stream, cudaStreamNonBlocking));
+    if (nin + nout > c->util_cap) {
+        if (c->util_dev) CU(cudaFree(c->util_dev));
+        c->util_dev = nullptr;
+        c->util_cap = 0;
+        const size_t cap = std::max<size_t>(nin + nout, 1u << 16);
+        CU(cudaMalloc((void **)&c->util_dev, sizeof(double) * cap));
+        c->util_cap = cap;
+    }
+    double *d_in = c->util_dev, *d_out = c->util_dev + nin;
+    CU(cudaMemcpyAsync(d_in, cube, sizeof(double) * nin, cudaMemcpyHostToDevice, c->util_stream));
+    CU(launch_prior(c->P, d_in, B, ld, flags, d_out, c->util_stream));
+    CU(cudaMemcpyAsync(theta_out, d_out, sizeof(double) * nout, cudaMemcpyDeviceToHost, c->util_stream));
+    CU(cudaStreamSynchronize(c->util_stream));
     c->kernel_launches += 1;
     return MCALF_OK;
 }
@@ -655,7 +721,7 @@ int mcalf_voigt_h(int device, int mode, const double *u, const double *a, int64_
     if (n == 0) return MCALF_OK;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(MCALF_E_NODEVICE, "no CUDA device");
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     double *d = nullptr;
     CU(cudaMalloc((void **)&d, sizeof(double) * 3 * (size_t)n));
     cudaError_t e = cudaMemcpy(d, u, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
@@ -671,7 +737,7 @@ int mcalf_ffma_peak(int device, double *tflops_out) {
     if (!tflops_out) return fail(MCALF_E_INVALID, "null output");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) return fail(MCALF_E_NODEVICE, "no CUDA device");
-    CU(cudaSetDevice(device));
+    ON_DEVICE(device);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     const int threads = 1024, grid = prop.multiProcessorCount * 2, iters = 4096;
@@ -700,7 +766,7 @@ int mcalf_ffma_peak(int device, double *tflops_out) {
 
 int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     if (!c || !out) return fail(MCALF_E_INVALID, "null argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     memset(out, 0, sizeof(*out));
     unsigned long long h[8];
     CU(cudaDeviceSynchronize());
@@ -715,6 +781,7 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
     out->evals_culled = h[4];
     out->evals_far = h[5];
     out->evals_core_precise = h[6];
+    out->evals_core_straddle = h[7];
     if (c->last_slot >= 0 || c->last_ring >= 0) {
         float ms = 0.f;
         Slot &s = c->last_slot == NBUF + 1 ? c->zc_slot : c->last_slot == NBUF ? c->dev_slot : (c->last_slot >= 0 ? c->slot[c->last_slot] : c->ring[c->last_ring]);
@@ -725,7 +792,7 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
 
 int mcalf_reset_stats(mcalf_ctx *c) {
     if (!c) return fail(MCALF_E_INVALID, "null context");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(cudaDeviceSynchronize());
     CU(cudaMemset(c->d_stats, 0, 8 * sizeof(unsigned long long)));
     c->kernel_launches = c->samples = c->samples_fp64 = 0;
@@ -734,7 +801,7 @@ int mcalf_reset_stats(mcalf_ctx *c) {
 
 int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
     if (!c || !name) return fail(MCALF_E_INVALID, "null argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     if (!strcmp(name, "cull_eps")) {
         if (!(value >= 0.0)) return fail(MCALF_E_INVALID, "cull_eps must be >= 0");
         c->P.eps_cull = (float)value;

@@ -22,10 +22,8 @@ struct DevProblem {
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
-    const float *delta_hi, *delta_lo;   // [npix] rho_i - rho_s(chunk) as a two-float
-    const float2 *delta2;               // [npix] the same, interleaved {hi, lo} (line-core pass, strong lines)
-    const float4 *delta4;               // [npix + 64] {hi[k], hi[k+32], lo[k], lo[k+32]}: pixel pairs of the packed core pass
-                                        // (zero where k+32 leaves the chunk)
+    const float2 *dhi2, *dlo2;          // [npix + 256] rho_i - rho_s(chunk) as a two-float (hi, lo), each stored as the pixel
+                                        // pair {v[i], v[i+32]} a lane holds (host_setup.h: build_pair_table)
     const float4 *obj_hi4, *obj_lo4, *w4; // [npix4/4] flux as a two-float and weight 1/err^2, four pixels per element;
                                         // obj = w = 0 on dropped pixels and on the padding
     const ChunkDesc *chunks;            // [nchunks]
@@ -51,7 +49,7 @@ struct BatchArgs {
 
 size_t fast_smem_bytes(const DevProblem &P, int nwarps);
 size_t fp64_smem_bytes(const DevProblem &P);
-cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes);
+cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes);
 cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm);
 cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st);
 cudaError_t launch_fp64(const DevProblem &P, const BatchArgs &Bt, const int *idx_list, const unsigned int *idx_count, int grid,

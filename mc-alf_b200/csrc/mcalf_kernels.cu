@@ -49,18 +49,23 @@ struct SampleHead {
     int nact;       // active (component, line) pairs + fillers
     int ncomp;      // int(p[startind])
     int nfill;      // fillers evaluated
-    int onecomp;    // 0: full vector; 1: reconstruct_onecomp; 2: reconstruct_onecomp_fill
+    int onecomp;    // 0: full vector; 1: reconstruct_onecomp; 2: reconstruct_onecomp_fill; 3: one line of one component
 };
+
+constexpr uint32_t MCALF_F_ROW5 = MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL | MCALF_F_ONELINE;   // rows [specres, cont, N, z, b(, line)]
+__device__ __forceinline__ int row_length(const DevProblem &P, uint32_t flags) {
+    return (flags & MCALF_F_ONELINE) ? 6 : (flags & MCALF_F_ROW5) ? 5 : P.ndim;
+}
 
 __device__ __forceinline__ SampleHead parse_head(const DevProblem &P, const double *th, uint32_t flags) {
     SampleHead h;
-    if (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) {
+    if (flags & MCALF_F_ROW5) {
         h.specres = th[0];
         h.cont = th[1];
-        h.onecomp = (flags & MCALF_F_ONECOMP_FILL) ? 2 : 1;
+        h.onecomp = (flags & MCALF_F_ONELINE) ? 3 : (flags & MCALF_F_ONECOMP_FILL) ? 2 : 1;
         h.ncomp = 1;
         h.nfill = 0;
-        h.nact = h.onecomp == 2 ? 1 : P.nlines;
+        h.nact = h.onecomp == 1 ? P.nlines : 1;
         return h;
     }
     h.onecomp = 0;
@@ -79,7 +84,12 @@ __device__ __forceinline__ void line_source(const DevProblem &P, const SampleHea
                                             double &logN, double &z, double &b, int &li) {
     if (h.onecomp) {
         logN = th[2]; z = th[3]; b = th[4];
-        li = h.onecomp == 2 ? P.nlines : t;
+        if (h.onecomp == 3) {          // th[5]: index into the line table (nlines = the filler line)
+            const double v = th[5];
+            li = (v >= 0.0 && v <= (double)P.nlines) ? (int)v : 0;
+        } else {
+            li = h.onecomp == 2 ? P.nlines : t;
+        }
         return;
     }
     const int ntarget = h.ncomp * P.nlines;
@@ -125,20 +135,6 @@ __device__ __forceinline__ int build_taps(const DevProblem &P, double specres, f
 // fast kernel
 // ---------------------------------------------------------------------------------------------
 constexpr int PX = 8;            // pixels per lane per chunk (chunk = 32 lanes x 8 = 256 pixels)
-
-// Pixels [k_lo, k_hi] of chunk `cd` that the core |u| < U_CORE_MARGIN of a line can reach (a superset:
-// the loop still tests every pixel), from the chunk's linear pixel <-> delta model; kslack (host computed)
-// bounds the model's error in pixels.  Empty when k_lo > k_hi.
-__device__ __forceinline__ void core_range(const ChunkDesc &cd, float iA, float U_hi, int &k_lo, int &k_hi) {
-    const float ka = ((-U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
-    const float kb = ((U_CORE_MARGIN - U_hi) * iA - cd.d0) * cd.inv_dstep;
-    float lo = fminf(ka, kb) - (float)cd.kslack, hi = fmaxf(ka, kb) + (float)cd.kslack;
-    if (!(lo == lo) || !(hi == hi)) { lo = 0.0f; hi = (float)CHUNK_PIXELS; }      // NaN: every pixel is a candidate
-    lo = fmaxf(lo, 0.0f);
-    hi = fminf(hi, (float)(cd.len - 1));
-    k_lo = (int)lo;
-    k_hi = (lo <= hi) ? (int)hi : -1;
-}
 
 constexpr int FF_NC = FF_DEG + 1;
 // The classification pass runs on P.vwarps "virtual warps" (a problem constant, not the CTA size): its
@@ -195,7 +191,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     for (int i = tid; i < MCALF_G1_N; i += nthreads) g1_smem[i] = g1_tab_dev[i];
     if (blockIdx.x == 0 && tid == 0) { Bt.clear_counters[0] = 0u; Bt.clear_counters[1] = 0u; }   // for the slot's next launch
     // per-thread statistics (only summed when Bt.stats != nullptr)
-    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0;
+    unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0, st_both = 0;
 
     for (;;) {
         // ---- next sample (dynamic: the active-component count varies per sample) ----
@@ -205,8 +201,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         const long long b = S.misc[0];
         if (b >= Bt.B) break;
         const double *row = Bt.params + b * Bt.ld;
-        const int nrow = (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) ? 5 : P.ndim;
-        if (tid < nrow) S.theta[tid] = load_theta(P, row, tid, flags);
+        const int nrow = row_length(P, flags);
+        for (int i = tid; i < nrow; i += nthreads) S.theta[i] = load_theta(P, row, i, flags);   // rows may be longer than the CTA
         __syncthreads();
         const SampleHead h = parse_head(P, S.theta, flags);
 
@@ -266,8 +262,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     for (int t = slot; t < h.nact; t += NS) {
                         const double U = S.A64[t] * (rho_s - S.rc64[t]);
                         const float Uh = (float)U;
-                        const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
-                        const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, P.eps_cull, P.eps_far) : -1;
+                        const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, ucm
+                        const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, L.w, P.eps_cull, P.eps_far) : -1;
                         if (cls == 3) farfield_accumulate(L.x, Uh, ds, L.z, L.y, C);
                         if (cls == 1 || cls == 2) {
                             uslice[t] = Uh;
@@ -308,14 +304,15 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             const float *fslice = P.scratch_in_flux ? S.flux + P.halo + cd.start + (c & 31) : S.farp + (size_t)c * (FF_NC * NS + 1);
             const float *uslice = P.scratch_in_flux ? fslice + (FF_NC * NS + 1) : S.uarr + (size_t)c * P.Lmax;
             // rows (32 consecutive pixels) are held in pairs: {row 2j, row 2j+1} in one 64-bit register pair,
-            // so the arithmetic below runs on the packed FFMA2 / FMUL2 forms
+            // so the arithmetic below runs on the packed FFMA2 / FMUL2 forms.  The pair tables are padded, so
+            // the loads need no bounds test (lanes beyond the chunk compute on finite junk nobody stores).
             constexpr int PX2 = PX / 2;
             F2 d[PX2], tau[PX2];
+            const float2 *dh2 = P.dhi2 + cd.start + lane;
 #pragma unroll
             for (int j = 0; j < PX2; ++j) {
-                const int k = 2 * j * 32 + lane;
-                d[j].x = (k < cd.len) ? __ldg(P.delta_hi + cd.start + k) : 0.0f;
-                d[j].y = (k + 32 < cd.len) ? __ldg(P.delta_hi + cd.start + k + 32) : 0.0f;
+                const float2 v = __ldg(dh2 + 64 * j);
+                d[j] = f2(v.x, v.y);
             }
             // far lines: sum the slots' partial expansions in slot order (lane n sums coefficient n),
             // broadcast, one polynomial per pixel
@@ -339,110 +336,73 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     for (int j = 0; j < PX2; ++j) tau[j] = fma2(tau[j], x[j], cn2);
                 }
             }
-            // near lines, direct wing form, in line order: 8 evaluations per lane per line; inside a line
-            // core the clamp makes it the constant wing_tau(c1, S_CUT), which the core pass below replaces
+            // near lines in line order, everything in registers.  A line whose core cannot reach the chunk
+            // takes the direct wing form on all eight rows.  A line that may have core pixels here is taken
+            // row pair by row pair: the warp votes whether the pair's 64 pixels are all beyond the line's core
+            // boundary (wing form), all inside the H1 table (core form -- it is the full Voigt function there,
+            // so it also serves the pixels just outside the boundary), or straddle both (both forms, per-pixel
+            // select).  No pixel index is ever dynamic, so tau never leaves the registers.
             const int MW = P.mwords;
-            unsigned anycore = 0;
             for (int w = 0; w < MW; ++w) {
-                anycore |= S.cmask[c * MW + w];
+                const unsigned cmw = S.cmask[c * MW + w];
                 for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
-                    const int t = (w << 5) + __ffs(m) - 1;
-                    const float4 L = *reinterpret_cast<const float4 *>(&S.lp[t]);   // A_hi, a2, c1, kappa
-                    const F2 A2 = f2(L.x), U2 = f2(uslice[t]), a22 = f2(L.y), c12 = f2(L.z);
+                    const int bit = __ffs(m) - 1;
+                    const int t = (w << 5) + bit;
+                    const float4 *lp4 = reinterpret_cast<const float4 *>(&S.lp[t]);
+                    const float4 r0 = lp4[0], r1 = lp4[1], r2 = lp4[2];
+                    LineP L;
+                    L.A_hi = r0.x; L.a2 = r0.y; L.c1 = r0.z; L.ucm = r0.w;
+                    L.cw0 = r1.x; L.cw1 = r1.y; L.cw2 = r1.z; L.cw3 = r1.w;
+                    L.cw4 = r2.x; L.scut = r2.y; L.kappa = r2.z; L.a = r2.w;
+                    const float Uh = uslice[t];
+                    const F2 A2 = f2(L.A_hi), U2 = f2(Uh), a22 = f2(L.a2);
+                    if (!((cmw >> bit) & 1u)) {
+#pragma unroll
+                        for (int j = 0; j < PX2; ++j) {
+                            const F2 u = fma2(A2, d[j], U2);
+                            tau[j] = wing_acc2(tau[j], fma2(u, u, a22), L);
+                        }
+                        continue;
+                    }
+                    L.A_lo = lp4[3].x;
+                    float Uh64, Ul;
+                    split2(S.A64[t] * (cd.rho_s - S.rc64[t]), Uh64, Ul);      // Uh64 == Uh
+                    const float2 *dl2 = P.dlo2 + cd.start + lane;
 #pragma unroll
                     for (int j = 0; j < PX2; ++j) {
                         const F2 u = fma2(A2, d[j], U2);
-                        F2 s2 = fma2(u, u, a22);
-                        s2.x = fmaxf(s2.x, S_CUT);
-                        s2.y = fmaxf(s2.y, S_CUT);
-                        tau[j] = add2(tau[j], wing_tau2(c12, s2));
-                    }
-                }
-            }
-            // line cores: only the pixels a core can reach.  The pixel index is dynamic, so tau is parked
-            // in shared memory for this pass -- in the chunk's own (still unused) slice of the depth
-            // buffer -- the cores are accumulated there, and tau comes back to registers afterwards.
-            if (anycore) {
-                float *tcore = S.flux + P.halo + cd.start;
-#pragma unroll
-                for (int j = 0; j < PX2; ++j) {
-                    const int k = 2 * j * 32 + lane;
-                    if (k < cd.len) tcore[k] = tau[j].x;
-                    if (k + 32 < cd.len) tcore[k + 32] = tau[j].y;
-                }
-                __syncwarp();
-                for (int w = 0; w < MW; ++w) {
-                    unsigned cm = S.cmask[c * MW + w];
-                    if (!cm) continue;
-                    // lane l prepares line 32 w + l (fp64 offset, its low part, the pixel range) ...
-                    float myUh = 0.f, myUl = 0.f;
-                    int myklo = 0, mykhi = -1;
-                    if ((cm >> lane) & 1u) {
-                        const int tl = (w << 5) + lane;
-                        split2(S.A64[tl] * (cd.rho_s - S.rc64[tl]), myUh, myUl);
-                        core_range(cd, S.lp[tl].iA, myUh, myklo, mykhi);
-                    }
-                    // ... and the warp takes the lines one at a time
-                    for (; cm; cm &= cm - 1) {
-                        const int src = __ffs(cm) - 1;
-                        const float Uh = __shfl_sync(0xffffffffu, myUh, src), Ul = __shfl_sync(0xffffffffu, myUl, src);
-                        const int k_lo = __shfl_sync(0xffffffffu, myklo, src), k_hi = __shfl_sync(0xffffffffu, mykhi, src);
-                        const LineP L = S.lp[(w << 5) + src];
-                        const float2 *dd = P.delta2 + cd.start;
-                        if (L.kappa <= KAPPA_LEAN) {          // warp-uniform: weak lines take the short core form
-                            // branch-free, 64 consecutive pixels per trip (two per lane in flight): the
-                            // loop is latency bound otherwise
-                            // (the delta table is padded by 64 entries, so the second load needs no bounds test)
-                            // delta4[k] = {hi[k], hi[k+32], lo[k], lo[k+32]}: the pair arrives packed
-                            const float4 *pa = P.delta4 + cd.start + k_lo + lane;
-                            float *ta_p = tcore + k_lo + lane;
-                            const F2 A2 = f2(L.A_hi), Al2 = f2(L.A_lo), Uh2 = f2(Uh), Ul2 = f2(Ul);
-#pragma unroll 1
-                            for (int ka = k_lo + lane; ka <= k_hi; ka += 64, pa += 64, ta_p += 64) {
-                                const bool vb = ka + 32 <= k_hi;
-                                const float4 dv = __ldg(pa);
-                                const F2 dh = f2(dv.x, dv.y), dl = f2(dv.z, dv.w);
-                                const F2 tc = f2(ta_p[0], vb ? ta_p[32] : 0.0f);
-                                const F2 u = fma2(A2, dh, Uh2);
-                                const F2 s2 = fma2(u, u, f2(L.a2));
-                                const bool ca = s2.x < S_CUT, cb = vb && s2.y < S_CUT;
-                                const F2 uc = add2(u, fma2(A2, dl, fma2(Al2, dh, Ul2)));
-                                const F2 hh = core_h32_lean2(L.a, L.a2, uc, g1_smem);
-                                const F2 v = add2(tc, fma2(f2(L.kappa), hh, f2(-L.c1w)));
-                                if (ca) ta_p[0] = v.x;
-                                if (cb) ta_p[32] = v.y;
-                                if (STATS) st_core += (ca ? 1 : 0) + (cb ? 1 : 0);
-                            }
-                        } else {
-#pragma unroll 1
-                            for (int k = k_lo + lane; k <= k_hi; k += 32) {
-                                const float2 dk = __ldg(dd + k);
-                                const float u = fma32(L.A_hi, dk.x, Uh);
-                                const float s = fma32(u, u, L.a2);
-                                if (s < S_CUT) {
-                                    float uh, ul;
-                                    core_u2(L.A_hi, L.A_lo, dk.x, dk.y, Uh, Ul, uh, ul);
-                                    tcore[k] += fma32(L.kappa, core_h32(L.a, L.a2, uh, ul, g1_smem), -L.c1w);
-                                    if (STATS) { st_core += 1; st_corep += 1; }
-                                }
-                            }
+                        const F2 s2 = fma2(u, u, a22);
+                        const bool all_wing = __all_sync(0xffffffffu, s2.x >= L.scut && s2.y >= L.scut);
+                        if (all_wing) {
+                            tau[j] = wing_acc2(tau[j], s2, L);
+                            continue;
                         }
+                        const bool all_tab = __all_sync(0xffffffffu, fabsf(u.x) <= U_TAB && fabsf(u.y) <= U_TAB);
+                        const float2 dlv = __ldg(dl2 + 64 * j);
+                        tau[j] = mixed_pair_tau(pair_kind(false, all_tab), tau[j], L, u, s2, d[j], f2(dlv.x, dlv.y), Uh64, Ul, g1_smem);
+                        if (STATS) { st_core += 2; st_corep += L.kappa > KAPPA_LEAN ? 2 : 0; st_both += all_tab ? 0 : 2; }
                     }
                 }
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < PX2; ++j) {
-                    const int k = 2 * j * 32 + lane;
-                    if (k < cd.len) tau[j].x = tcore[k];
-                    if (k + 32 < cd.len) tau[j].y = tcore[k + 32];
-                }
             }
+            __syncwarp();        // the chunk's pass-A scratch (read above) lives where its depth goes now
+            {
+                float *dst = S.flux + P.halo + cd.start + lane;
+                if (cd.len == CHUNK_PIXELS) {
 #pragma unroll
-            for (int j = 0; j < PX2; ++j) {
-                const int k = 2 * j * 32 + lane;
-                const F2 dep = depth32_2(tau[j]);
-                if (k < cd.len) S.flux[P.halo + cd.start + k] = dep.x;
-                if (k + 32 < cd.len) S.flux[P.halo + cd.start + k + 32] = dep.y;
+                    for (int j = 0; j < PX2; ++j) {
+                        const F2 dep = depth32_2(tau[j]);
+                        dst[64 * j] = dep.x;
+                        dst[64 * j + 32] = dep.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < PX2; ++j) {
+                        const int k = 2 * j * 32 + lane;
+                        const F2 dep = depth32_2(tau[j]);
+                        if (k < cd.len) dst[64 * j] = dep.x;
+                        if (k + 32 < cd.len) dst[64 * j + 32] = dep.y;
+                    }
+                }
             }
             __syncwarp();
         }
@@ -551,6 +511,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         st_total = (unsigned long long)warp_sum((double)st_total);
         st_far = (unsigned long long)warp_sum((double)st_far);
         st_corep = (unsigned long long)warp_sum((double)st_corep);
+        st_both = (unsigned long long)warp_sum((double)st_both);
         if (lane == 0) {
             atomicAdd(Bt.stats + 0, st_total);
             atomicAdd(Bt.stats + 1, st_wing);
@@ -559,6 +520,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             atomicAdd(Bt.stats + 4, st_cull);
             atomicAdd(Bt.stats + 5, st_far);
             atomicAdd(Bt.stats + 6, st_corep);
+            atomicAdd(Bt.stats + 7, st_both);
         }
     }
 }
@@ -588,8 +550,8 @@ mcalf_fp64_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         const long long b = idx_list ? idx_list[it] : it;
         __syncthreads();
         const double *row = Bt.params + b * Bt.ld;
-        const int nrow = (flags & (MCALF_F_ONECOMP | MCALF_F_ONECOMP_FILL)) ? 5 : P.ndim;
-        if (tid < nrow) theta[tid] = load_theta(P, row, tid, flags);
+        const int nrow = row_length(P, flags);
+        for (int i = tid; i < nrow; i += nthreads) theta[i] = load_theta(P, row, i, flags);
         __syncthreads();
         const SampleHead h = parse_head(P, theta, flags);
         for (int t = tid; t < h.nact; t += nthreads) {
@@ -685,7 +647,9 @@ __global__ void mcalf_voigt_h_kernel(int mode, const double *u, const double *a,
     {
         if (mode == 1) { out[i] = voigt_h64(a[i], u[i]); continue; }
         const float af = (float)a[i], uf = (float)u[i];
-        // mode 0: wing form / two-float core form; mode 2: wing form / the short core form of weak lines
+        // mode 0: wing form / two-float core form; mode 2: wing form / the short core form of weak lines;
+        // mode 3: the weak-line forms with the core boundary drawn in to s = S_WIDE
+        if (mode == 3) { out[i] = (double)voigt_h32_weak(af, uf, MCALF_S_WIDE); continue; }
         if (mode == 2 && fma32(uf, uf, af * af) < S_CUT) out[i] = (double)core_h32_lean(af, af * af, uf);
         else out[i] = (double)voigt_h32(af, uf);
     }
@@ -722,14 +686,26 @@ size_t fp64_smem_bytes(const DevProblem &P) {
     return sizeof(double) * ((size_t)P.ndim_pad + 4 * (size_t)P.Lmax + P.nmax + 1 + 64 + P.npix);
 }
 
-cudaError_t configure_kernels(size_t fast_bytes, size_t fp64_bytes) {
-    cudaError_t e = cudaFuncSetAttribute(mcalf_fast_kernel<false, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+// cudaFuncAttributeMaxDynamicSharedMemorySize is held per function and per device, not per context: raise it
+// to what the device allows (opt-in limit minus the kernel's static shared memory) and never to one problem's
+// size, so contexts of different sizes on one device cannot lower each other's limit.  Idempotent.
+template <typename K>
+static cudaError_t raise_smem_limit(K kernel, size_t optin, size_t *static_bytes) {
+    cudaFuncAttributes at;
+    cudaError_t e = cudaFuncGetAttributes(&at, kernel);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mcalf_fast_kernel<true, 1024, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    if (static_bytes) *static_bytes = at.sharedSizeBytes;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(optin - at.sharedSizeBytes));
+}
+
+cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes) {
+    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, 1024, 1>, optin_bytes, fast_static_bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(mcalf_fast_kernel<false, 256, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_bytes);
+    e = raise_smem_limit(mcalf_fast_kernel<true, 1024, 1>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(mcalf_fp64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp64_bytes);
+    e = raise_smem_limit(mcalf_fast_kernel<false, 256, 5>, optin_bytes, nullptr);
+    if (e != cudaSuccess) return e;
+    return raise_smem_limit(mcalf_fp64_kernel, optin_bytes, nullptr);
 }
 
 // dense = the 48-register build (CTAs of at most 256 threads, five or more per SM)

@@ -5,10 +5,13 @@
 // Reference being replaced: als_fitter.voigt_tau (mcalf/routines/hires_fitter.py:331-367), whose
 // kernel is  tau = 0.014971475 * N * f * Re w(u + i a) / dnu  with w from scipy.special.wofz.
 //
-//   fp32 fast path   H(a,u) = Re w(u+ia) split at s = u^2 + a^2 = S_CUT (= 36):
-//       wing  (s >= S_CUT):  H = (a/sqrt pi) * q * P(q),  q = 1/s, P a degree-4 polynomial
-//                            (1 MUFU.RCP + 6 FMA-pipe ops, relative error 2e-8 + rounding)
-//       core  (s <  S_CUT):  Taylor series in a about the Gaussian (Harris 1948):
+//   fp32 fast path   H(a,u) = Re w(u+ia) split at s = u^2 + a^2 = scut, a per-line boundary
+//                    (S_CUT = 36 for strong lines; drawn in to max(16, ln kappa + 17.5) for weak lines,
+//                    whose Gaussian part kappa exp(-s) is below 2.5e-8 beyond it -- line_cut):
+//       wing  (s >= scut):   H = (a/sqrt pi) * q * P(q),  q = 1/s, P a degree-4 polynomial
+//                            (1 MUFU.RCP + 6 FMA-pipe ops; fitted over s >= 36 to 6e-8 for strong lines,
+//                            over s >= 16 to 5e-6 for weak lines where 5e-6 * tau_wing <= 1e-8)
+//       core  (s <  scut):   Taylor series in a about the Gaussian (Harris 1948):
 //                            H = G0 (1 + a^2 (1-2x)) + a (G1 (1 + a^2 (1 - 2x/3)) + 2 a^2/(3 sqrt pi)),
 //                            x = u^2, G0 = exp(-x) from a two-float x, G1 = H1(u) from a Taylor table.
 //                            Valid for a <= A_MAX_FAST; larger a is routed to the fp64 path.
@@ -20,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define MCALF_HD __host__ __device__ __forceinline__
+#define MCALF_HD_NOINLINE __host__ __device__ __noinline__
 #else
 #define MCALF_HD inline
+#define MCALF_HD_NOINLINE inline
 #endif
 
 #include "voigt_tables.inc"
@@ -224,12 +229,14 @@ MCALF_HD float ex2_32(float t) {
 // Gaussian through MUFU.EX2 (relative error 2^-22).  The optical-depth error is <= ~3e-7 tau, i.e. a
 // flux error <= 1.5e-7 for kappa <= KAPPA_LEAN (the flux sensitivity F |dtau| peaks near tau = 1).
 constexpr float KAPPA_LEAN = 8.0f;
+constexpr float U_TAB_END = MCALF_G1_UMAX + 0.03f;   // last H1 table row
+constexpr float U_TAB = MCALF_G1_UMAX;               // |u| up to which the core forms are valid
 MCALF_HD float core_h32_lean(float a, float a2, float u, const G1Row *tab = nullptr) {
     const float x = u * u;
     const float g0 = ex2_32(x * -1.44269504088896341f);
     const float au = fabsf(u);
     int j;
-    const float fj = rn_mul(fminf(au, 6.03f), (float)MCALF_G1_INV_H, j);     // (the table ends at u = 6.03)
+    const float fj = rn_mul(fminf(au, U_TAB_END), (float)MCALF_G1_INV_H, j);   // (the table ends at U_TAB_END)
     const float d = fma32(fj, -1.0f / (float)MCALF_G1_INV_H, au);
     const G1Row t = g1_row(j, tab);
     const float g1 = fma32(fma32(fma32(t.c3, d, t.c2), d, t.c1), d, t.c0);
@@ -246,7 +253,7 @@ MCALF_HD F2 core_h32_lean2(float a, float a2, F2 u, const G1Row *tab = nullptr) 
     const F2 t = mul2(x, f2(-1.44269504088896341f));
     const F2 g0 = f2(ex2_32(t.x), ex2_32(t.y));
     const F2 au = f2(fabsf(u.x), fabsf(u.y));
-    const F2 ac = f2(fminf(au.x, 6.03f), fminf(au.y, 6.03f));                // (the table ends at u = 6.03)
+    const F2 ac = f2(fminf(au.x, U_TAB_END), fminf(au.y, U_TAB_END));        // (the table ends at U_TAB_END)
     const F2 tm = fma2(ac, f2((float)MCALF_G1_INV_H), f2(RN_MAGIC));         // rn_mul, packed
     const F2 fj = add2(tm, f2(-RN_MAGIC));
     union { float f; int32_t i; } ua, ub;
@@ -264,12 +271,25 @@ MCALF_HD F2 core_h32_lean2(float a, float a2, F2 u, const G1Row *tab = nullptr) 
     return fma2(g0, k0, mul2(f2(a), inner));
 }
 
-// Convenience scalar form of the fast path (unit tests, mcalf_voigt_h): u, a as floats.
+// Convenience scalar forms of the fast path (unit tests, mcalf_voigt_h): u, a as floats.
 MCALF_HD float voigt_h32(float a, float u) {
     float a2 = a * a;
     float s = fma32(u, u, a2);
     if (s < S_CUT) return core_h32(a, a2, u, 0.0f);
     return a * 0.564189584f * wing_qp(s);
+}
+// weak-line forms: wide-interval wing polynomial beyond scut (>= S_WIDE), short core form inside
+MCALF_HD float voigt_h32_weak(float a, float u, float scut) {
+    const float w[5] = MCALF_WING_PW;
+    float a2 = a * a;
+    float s = fma32(u, u, a2);
+    if (s < scut) return core_h32_lean(a, a2, u);
+    float q = rcp32(s);
+    float p = fma32(w[4], q, w[3]);
+    p = fma32(p, q, w[2]);
+    p = fma32(p, q, w[1]);
+    p = fma32(p, q, w[0]);
+    return a * 0.564189584f * (p * q);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -341,10 +361,13 @@ struct Line64 {
     double A, rc, kappa, a;
 };
 
-// 32 bytes: what the mixed (core-containing) path reads per line
-struct LineP {
-    float A_hi, a2, c1, kappa;   // c1 = kappa*a/sqrt(pi): the wing amplitude
-    float A_lo, a, c1w, iA;      // c1w = wing value at s = S_CUT (what the clamped direct form adds inside a core); iA = 1/A
+// 64 bytes per active line, four float4 rows: pass A reads row 0, the direct wing form rows 0-2, the
+// line-core forms all four.
+struct alignas(16) LineP {
+    float A_hi, a2, c1, ucm;     // c1 = kappa*a/sqrt(pi): the wing amplitude; ucm: a chunk whose |u| stays above it is wing only
+    float cw0, cw1, cw2, cw3;    // c1 * (wing polynomial of this line): tau_wing = q (cw0 + q (cw1 + ...)), q = 1/s
+    float cw4, scut, kappa, a;   // scut: the line's core boundary in s = u^2 + a^2
+    float A_lo, pad0, pad1, pad2;
 };
 
 MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, double f, double gamma,
@@ -369,21 +392,41 @@ MCALF_HD void split2(double v, float &hi, float &lo) {
     lo = (float)(v - (double)hi);
 }
 
-MCALF_HD LineP line_pack(const Line64 &L) {
+// Per-line core boundary.  Outside s = scut the wing form drops the Gaussian part of H, an optical-depth
+// error of at most kappa exp(-scut): scut = ln(kappa) + ln(1/EPS_GAUSS) keeps it below EPS_GAUSS.  The
+// boundary may only be drawn inside S_CUT when the wide-interval wing polynomial is accurate enough
+// for this line (its relative error times the wing's optical depth at the boundary <= EPS_WING);
+// otherwise the line keeps S_CUT and the narrow-interval polynomial.
+constexpr double EPS_GAUSS = 2.5e-8;
+constexpr double LN_INV_EPS_GAUSS = 17.504390;     // ln(1 / 2.5e-8)
+constexpr double EPS_WING = 1.0e-8;
+constexpr float U_CUT_MARGIN = 0.01f;              // covers the one-FMA coordinate's error
+constexpr float U_CORE_MARGIN = 6.01f;             // sqrt(S_CUT) + U_CUT_MARGIN
+
+MCALF_HD bool line_cut(double kappa, double a, float &scut) {
+    const double c1 = kappa * a / SQRTPI_D;
+    double s = (kappa > 0.0) ? log(kappa) + LN_INV_EPS_GAUSS : (double)MCALF_S_WIDE;
+    if (!(s > (double)MCALF_S_WIDE)) s = (double)MCALF_S_WIDE;
+    const bool wide = s < (double)S_CUT - 0.5 && c1 * MCALF_WING_PW_ERR <= EPS_WING * s;
+    scut = wide ? (float)s : S_CUT;
+    return wide;
+}
+
+MCALF_HD LineP line_pack_full(const Line64 &L) {
+    const float wn[5] = MCALF_WING_P, ww[5] = MCALF_WING_PW;
     LineP o;
     split2(L.A, o.A_hi, o.A_lo);
     o.a = (float)L.a;
     o.a2 = (float)(L.a * L.a);
     o.c1 = (float)(L.kappa * L.a / SQRTPI_D);
     o.kappa = (float)L.kappa;
-    o.c1w = 0.0f;
-    o.iA = (float)(1.0 / L.A);
+    const bool wide = line_cut(L.kappa, L.a, o.scut);
+    o.ucm = wide ? sqrtf(o.scut) + U_CUT_MARGIN : U_CORE_MARGIN;
+    const float *w = wide ? ww : wn;
+    o.cw0 = o.c1 * w[0]; o.cw1 = o.c1 * w[1]; o.cw2 = o.c1 * w[2]; o.cw3 = o.c1 * w[3]; o.cw4 = o.c1 * w[4];
+    o.pad0 = o.pad1 = o.pad2 = 0.0f;
     return o;
 }
-
-// |u| below which a chunk is treated as containing line-core pixels (S_CUT = 36 plus a margin that
-// covers the one-FMA coordinate's error).
-constexpr float U_CORE_MARGIN = 6.01f;
 
 // Far-field ("local expansion") of the Lorentzian wings.  For a line whose centre lies far outside a
 // chunk, tau(delta) = c1 g(U + A delta), g(u) = 1/u^2 + (3/2 - a^2)/u^4 + (15/4)/u^6 (the asymptotic
@@ -399,12 +442,12 @@ constexpr float FF_UMIN = 10.0f;
 constexpr float FF_TRUNC = 2.0f * (FF_DEG + 2) / ((1.0f - 0.45f) * (1.0f - 0.45f));
 
 // Class of a (line, chunk) pair: 0 = culled, 1 = wing only, 2 = mixed (some pixel may have
-// u^2 + a^2 < S_CUT), 3 = far field.  ds = max |delta| over the chunk.
-MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float eps_cull, float eps_far) {
+// u^2 + a^2 < scut, i.e. |u| < ucm), 3 = far field.  ds = max |delta| over the chunk.
+MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float ucm, float eps_cull, float eps_far) {
     const float hw = A_hi * ds;                  // half-width of the chunk in u
     const float aU = fabsf(U_hi);
     const float umin = aU - hw;
-    if (!(umin > U_CORE_MARGIN)) return 2;       // also catches NaN
+    if (!(umin > ucm)) return 2;                 // also catches NaN
     const float um2 = umin * umin;
     // tau <= c1 q P(q) <= 1.05 c1 / u^2 on the chunk
     if (1.05f * c1 < eps_cull * um2) return 0;
@@ -452,32 +495,21 @@ MCALF_HD float farfield_eval(const float *C, float x) {
     return p;
 }
 
-// one wing evaluation: tau contribution of a line at s = u^2 + a^2 >= S_CUT
-MCALF_HD float wing_tau(float c1, float s) {
-    const float w[5] = MCALF_WING_P;
-    float q = rcp32(s);
-    float p = fma32(w[4], q, w[3]);
-    p = fma32(p, q, w[2]);
-    p = fma32(p, q, w[1]);
-    p = fma32(p, q, w[0]);
-    return (c1 * q) * p;
+// The direct wing form of one line on a pair of pixels: q (cw0 + q (cw1 + q (cw2 + q (cw3 + q cw4)))), q = 1/s,
+// with the line's pre-scaled coefficients.  s >= scut (guaranteed by the caller's classification, or clamped).
+MCALF_HD F2 wing_val2(F2 s, const LineP &L, F2 &q) {
+    q = f2(rcp32(s.x), rcp32(s.y));
+    F2 p = fma2(f2(L.cw4), q, f2(L.cw3));
+    p = fma2(p, q, f2(L.cw2));
+    p = fma2(p, q, f2(L.cw1));
+    p = fma2(p, q, f2(L.cw0));
+    return p;
 }
-
-MCALF_HD LineP line_pack_full(const Line64 &L) {
-    LineP o = line_pack(L);
-    o.c1w = wing_tau(o.c1, S_CUT);
-    return o;
-}
-
-// the wing form on a pair of pixels; s2 already clamped where needed
-MCALF_HD F2 wing_tau2(F2 c1, F2 s) {
-    const float w[5] = MCALF_WING_P;
-    const F2 q = f2(rcp32(s.x), rcp32(s.y));
-    F2 p = fma2(f2(w[4]), q, f2(w[3]));
-    p = fma2(p, q, f2(w[2]));
-    p = fma2(p, q, f2(w[1]));
-    p = fma2(p, q, f2(w[0]));
-    return mul2(mul2(c1, q), p);
+// tau + wing (the last multiply fused with the accumulation)
+MCALF_HD F2 wing_acc2(F2 tau, F2 s, const LineP &L) {
+    F2 q;
+    const F2 p = wing_val2(s, L, q);
+    return fma2(q, p, tau);
 }
 
 // two-float u = A*delta + U for the line core
@@ -494,19 +526,45 @@ MCALF_HD void core_u2(float A_hi, float A_lo, float d_hi, float d_lo, float U_hi
     ul = se + (pl + U_lo);
 }
 
-// tau contribution of one line at one pixel of a mixed chunk
-MCALF_HD float mixed_tau(const LineP &L, float U_hi, float U_lo, float d_hi, float d_lo, bool &core) {
-    const float u = fma32(L.A_hi, d_hi, U_hi);
-    const float s = fma32(u, u, L.a2);
-    core = s < S_CUT;
-    if (!core) return wing_tau(L.c1, s);
-    if (L.kappa <= KAPPA_LEAN) {
-        const float uc = u + fma32(L.A_hi, d_lo, fma32(L.A_lo, d_hi, U_lo));
-        return L.kappa * core_h32_lean(L.a, L.a2, uc);
-    }
+// strong lines (rare): one out-of-line copy, so that the unrolled synthesis loop stays small
+MCALF_HD_NOINLINE float core_precise(float A_hi, float A_lo, float d_hi, float d_lo, float U_hi, float U_lo, float a, float a2,
+                                     const G1Row *tab) {
     float uh, ul;
-    core_u2(L.A_hi, L.A_lo, d_hi, d_lo, U_hi, U_lo, uh, ul);
-    return L.kappa * core_h32(L.a, L.a2, uh, ul);
+    core_u2(A_hi, A_lo, d_hi, d_lo, U_hi, U_lo, uh, ul);
+    return core_h32(a, a2, uh, ul, tab);
+}
+
+// kappa H(a,u) of one line on a pair of pixels with the line-core forms (valid for |u| <= U_TAB): the short
+// form for weak lines, the two-float form for strong ones.  u = fma(A_hi, d_hi, U_hi) is passed in.
+MCALF_HD F2 core_val2(const LineP &L, F2 u, F2 dh, F2 dl, float U_hi, float U_lo, const G1Row *tab = nullptr) {
+    F2 h;
+    if (L.kappa <= KAPPA_LEAN) {
+        const F2 uc = add2(u, fma2(f2(L.A_hi), dl, fma2(f2(L.A_lo), dh, f2(U_lo))));
+        h = core_h32_lean2(L.a, L.a2, uc, tab);
+    } else {
+        h.x = core_precise(L.A_hi, L.A_lo, dh.x, dl.x, U_hi, U_lo, L.a, L.a2, tab);
+        h.y = core_precise(L.A_hi, L.A_lo, dh.y, dl.y, U_hi, U_lo, L.a, L.a2, tab);
+    }
+    return mul2(f2(L.kappa), h);
+}
+
+// What the kernel does with one mixed line on one pair of 32-pixel rows (the 64 lanes' values are passed as
+// arrays by the host emulation; the kernel votes across the warp): all pixels beyond the core boundary ->
+// wing form; all pixels inside the H1 table -> core form (valid on both sides of the boundary); a pair that
+// straddles both -> both forms and a per-pixel select.  Returns 0 / 1 / 2 for the statistics.
+enum { PAIR_WING = 0, PAIR_CORE = 1, PAIR_BOTH = 2 };
+MCALF_HD int pair_kind(bool all_wing, bool all_tab) { return all_wing ? PAIR_WING : (all_tab ? PAIR_CORE : PAIR_BOTH); }
+
+MCALF_HD F2 mixed_pair_tau(int kind, F2 tau, const LineP &L, F2 u, F2 s, F2 dh, F2 dl, float U_hi, float U_lo,
+                           const G1Row *tab = nullptr) {
+    if (kind == PAIR_WING) return wing_acc2(tau, s, L);
+    const F2 kh = core_val2(L, u, dh, dl, U_hi, U_lo, tab);
+    if (kind == PAIR_CORE) return add2(tau, kh);
+    F2 q;
+    const F2 sc = f2(fmaxf(s.x, L.scut), fmaxf(s.y, L.scut));
+    const F2 p = wing_val2(sc, L, q);
+    const F2 w = mul2(q, p);
+    return add2(tau, f2(s.x < L.scut ? kh.x : w.x, s.y < L.scut ? kh.y : w.y));
 }
 
 // LSF geometry (hires_fitter.py:452-459): sigma in pixels and half-width n = ceil(3.0348 sigma).

@@ -353,10 +353,10 @@ class als_fitter:
             raise ValueError("rows have %d entries, need %d" % (A.shape[1], width))
         return A, A.shape[0], A.shape[1], False
 
-    @staticmethod
-    def _stream():
+    def _stream(self):
+        """torch's current stream ON THE FITTER'S DEVICE (not on torch's current device)."""
         import torch
-        return torch.cuda.current_stream().cuda_stream
+        return torch.cuda.current_stream(self.device).cuda_stream
 
     def lnlhood_batch(self, P, unit_cube=False, fp64=None, return_chi2=False, no_trunc=False):
         """logL of every row of ``P`` (physical parameters, or unit-cube draws with ``unit_cube``):
@@ -438,17 +438,22 @@ class als_fitter:
             cube[ii] = cube[ii] * self._ptp[ii] + self._blo[ii]
         return cube
 
-    def lnprior(self, p):                                                # :218-234
-        if all(b[0] <= v <= b[1] for v, b in zip(p, self.bounds)):
-            pav = 0
-            if self.Gpriors is not None:
-                for par in range(len(p)):
-                    if self.Gpriors[2 * par] != 'none' and self.Gpriors[(2 * par) + 1] != 'none':
-                        val = float(self.Gpriors[2 * par])
-                        sig = float(self.Gpriors[(2 * par) + 1])
-                        pav += -0.5 * (((p[par] - val) / sig) ** 2 + np.log(2. * np.pi * sig ** 2))
-            return pav
-        return -np.inf
+    def lnprior(self, p):
+        """log prior density up to the box normalisation (the quantity hires_fitter.py:218-234 returns):
+        -inf outside the bounds; inside, 0 plus a Gaussian term for every parameter whose (value, sigma)
+        pair in ``Gpriors`` (flat list, two entries per parameter, the string 'none' = no term) is given."""
+        theta = np.asarray([p[i] for i in range(self.ndim)], dtype=np.float64)
+        if np.any(theta < self._blo) or np.any(theta > self._bhi) or np.any(np.isnan(theta)):
+            return -np.inf
+        if self.Gpriors is None:
+            return 0
+        pairs = [(self.Gpriors[2 * i], self.Gpriors[2 * i + 1]) for i in range(self.ndim)]
+        idx = [i for i, (m, sd) in enumerate(pairs) if m != 'none' and sd != 'none']
+        if not idx:
+            return 0
+        mu = np.array([float(pairs[i][0]) for i in idx])
+        sd = np.array([float(pairs[i][1]) for i in idx])
+        return float(np.sum(-0.5 * (((theta[idx] - mu) / sd) ** 2 + np.log(2.0 * np.pi * sd ** 2))))
 
     def _row(self, p, n=None):
         n = self.ndim if n is None else n
@@ -512,37 +517,30 @@ class als_fitter:
     # introduced) and sum over ncompmax components; here the current layout is used (components at
     # 1+3k+startind) and only the int(p[startind]) active components count.
     # ------------------------------------------------------------------------------------------
-    def _single_line_fitter(self, lineid):
-        cache = self.__dict__.setdefault("_line_fitters", {})
-        if lineid not in cache:
-            lp = self.linepars[lineid]
-            name = "line%d" % lineid
-            cache[lineid] = als_fitter((self.obj_wl, self.obj, self.obj_noise), [[self.obj_wl.min() - 1.0, self.obj_wl.max() + 1.0]],
-                                       [name], [1, 1], specres=[0.0], contval=[1.0], device=self.device,
-                                       atomic={name: (lp["wrest"].value, lp["f"], lp["gamma"].value)})
-        return cache[lineid]
+    def reconstruct_oneline_batch(self, rows6, fp64=None, dtype=np.float64):
+        """Rows ``[specres, continuum, N, z, b, line]`` -> flux of ONE line (index into ``linepars``;
+        ``numlines`` = the filler line) of one component: the single-line ``voigt_model`` of :369-377."""
+        rows, B, ld, on_dev = self._rows(rows6, 6)
+        return self._model(rows, B, ld, on_dev, self._flags(False, fp64) | capi.F_ONELINE, dtype)
 
     def calc_w_batch(self, P, lineid=0, max_rows=4096):
         """Rest-frame equivalent width of line ``lineid`` summed over the active components, per row of
         ``P`` (batched ``calc_w``, :467-491): sum_k sum_i (1 - T_k(lambda_i)) dlambda_i / (1 + z_k), with the
-        unconvolved single-line transmission from the CUDA model kernel."""
+        unconvolved single-line transmission from the CUDA model kernel (this context, MCALF_F_ONELINE)."""
         P = np.ascontiguousarray(np.atleast_2d(np.asarray(P, dtype=np.float64)))
-        f1 = self._single_line_fitter(lineid)
         dl = np.diff(self.obj_wl)
         dl = np.insert(dl, 0, dl[0])                                       # :486-487
-        s = self.startind
+        s, nmax = self.startind, self.ncompmax
+        nact = np.clip(np.nan_to_num(P[:, s]).astype(np.int64), 0, nmax)
+        comps = P[:, 1 + s:1 + s + 3 * nmax].reshape(-1, nmax, 3)
+        owner, slot = np.nonzero(np.arange(nmax)[None, :] < nact[:, None])   # (sample, component) of every active one
+        rows = np.empty((owner.size, 6), dtype=np.float64)
+        rows[:, 0], rows[:, 1], rows[:, 5] = 0.0, 1.0, float(lineid)         # specres 0: no LSF; continuum 1
+        rows[:, 2:5] = comps[owner, slot]
         out = np.zeros(P.shape[0])
-        rows, owner, zs = [], [], []
-        for i, p in enumerate(P):
-            for k in range(min(max(int(p[s]), 0), self.ncompmax)):
-                N, z, b = p[1 + 3 * k + s:4 + 3 * k + s]
-                rows.append((0.0, 1.0, N, z, b))
-                owner.append(i)
-                zs.append(z)
-        rows, owner, zs = np.array(rows, dtype=np.float64).reshape(-1, 5), np.array(owner, dtype=int), np.array(zs)
         for lo in range(0, len(rows), max_rows):
-            flux = f1.reconstruct_onecomp_batch(rows[lo:lo + max_rows])
-            w = ((1.0 - flux) * dl[None, :]).sum(axis=1) / (1.0 + zs[lo:lo + max_rows])
+            flux = self.reconstruct_oneline_batch(rows[lo:lo + max_rows])
+            w = ((1.0 - flux) * dl[None, :]).sum(axis=1) / (1.0 + rows[lo:lo + max_rows, 3])
             np.add.at(out, owner[lo:lo + max_rows], w)
         return out
 

@@ -15,7 +15,34 @@ small protocol each sampler uses, are import-guarded, and are tested against fak
                        a continuous uniform and floors it (``cli.py:251``, ``hires_fitter.py:616``);
                        the kernel's ``int()`` of that slot does the same for non-negative values.
 """
+import logging
+
 import numpy as np
+
+
+_UNWRAP_ATTRS = ("__wrapped__", "func", "loglikelihood", "prior_transform", "fn", "f")
+
+
+def _unwrap_candidates(func, depth=4):
+    """``func`` and whatever callables sampler-side wrappers hide it behind: dynesty's
+    ``_function_wrapper`` (``.func``), ``functools.partial`` (``.func``/``.args[0]``), ``functools.wraps``
+    (``__wrapped__``), objects carrying ``.loglikelihood`` / ``.prior_transform``."""
+    seen, todo = [], [(func, 0)]
+    while todo:
+        f, d = todo.pop()
+        if f is None or any(f is g for g in seen):
+            continue
+        seen.append(f)
+        if d >= depth:
+            continue
+        for name in _UNWRAP_ATTRS:
+            inner = getattr(f, name, None)
+            if callable(inner):
+                todo.append((inner, d + 1))
+        args = getattr(f, "args", None)
+        if isinstance(args, tuple) and args and callable(args[0]):
+            todo.append((args[0], d + 1))
+    return seen
 
 
 class BatchPool:
@@ -23,16 +50,23 @@ class BatchPool:
         self.fitter = fitter
         self.size = size or 1
         self.launches = 0
+        self.scalar_fallbacks = 0
+        self._warned = False
 
     def _is(self, func, *names):
-        target = getattr(func, "__func__", func)
+        """True when ``func`` (possibly wrapped) is one of this fitter's bound methods ``names``."""
+        targets = []
         for name in names:
-            bound = getattr(self.fitter, name)
-            if target is getattr(bound, "__func__", bound) and getattr(func, "__self__", self.fitter) is self.fitter:
+            bound = getattr(self.fitter, name, None)
+            if bound is not None:
+                targets.append(getattr(bound, "__func__", bound))
+        for f in _unwrap_candidates(func):
+            if getattr(f, "__self__", None) is self.fitter and getattr(f, "__func__", f) in targets:
                 return True
-        # dynesty wraps callables (e.g. _function_wrapper with .func); unwrap one level
-        inner = getattr(func, "func", None)
-        return inner is not None and inner is not func and self._is(inner, *names)
+        return False
+
+    def _owned(self, func):
+        return any(getattr(f, "__self__", None) is self.fitter for f in _unwrap_candidates(func))
 
     def map(self, func, iterable):
         pts = list(iterable)
@@ -47,6 +81,13 @@ class BatchPool:
         if self._is(func, "_scale_cube_pc"):
             self.launches += 1
             return list(self.fitter.prior_transform_batch(np.asarray(pts, dtype=np.float64)))
+        if self._owned(func):
+            # a method of OUR fitter that has no batched form here: correct, but one launch per point
+            self.scalar_fallbacks += 1
+            if not self._warned:
+                self._warned = True
+                logging.getLogger(__name__).warning(
+                    "BatchPool: %r belongs to the fitter but has no batched form; mapping it point by point", func)
         return list(map(func, pts))
 
     # context-manager / lifecycle no-ops some samplers call on a pool

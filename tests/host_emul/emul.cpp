@@ -38,63 +38,94 @@ int emul_num_chunks(long npix, const double *wave) {
     return (int)chunks.size();
 }
 
-// Optical depth of `nlines` lines over the pixel grid exactly as mcalf_fast_kernel accumulates it
-// (chunk classification, one-FMA wing coordinate, two-float core coordinate).  lines: rows of
-// (logN, z, b_kms, wrest, f, gamma).  cls_out (nullable): [nchunks*nlines] class of each pair.
+void emul_voigt_h32_weak(long n, const double *a, const double *u, double scut, double *out) {
+    for (long i = 0; i < n; ++i) out[i] = (double)voigt_h32_weak((float)a[i], (float)u[i], (float)scut);
+}
+
+// scut / wide flag the kernel picks for a line of given kappa, a
+int emul_line_cut(double kappa, double a, double *scut) {
+    float sc;
+    const bool wide = line_cut(kappa, a, sc);
+    *scut = (double)sc;
+    return wide ? 1 : 0;
+}
+
+// Optical depth of `nlines` lines over the pixel grid exactly as mcalf_fast_kernel accumulates it:
+// per chunk the far-field polynomial first, then the near lines in line order -- wing-only lines on the
+// direct wing form, lines whose core may reach the chunk row pair by row pair (64 pixels: the warp's vote
+// is a loop over the pair's 64 slots here, junk slots beyond a short chunk included, as in the kernel).
+// lines: rows of (logN, z, b_kms, wrest, f, gamma).  cls_out (nullable): [nchunks*nlines] class of each
+// pair.  kind_out (nullable): [4] row pairs taken as wing / core / straddling, and wing-only line-chunks.
 void emul_tau(long npix, const double *wave, int nlines, const double *lines, double eps_cull, double eps_far,
-              double *tau_out, int *cls_out) {
+              double *tau_out, int *cls_out, long *kind_out) {
     const double lam_ref = wave[npix / 2];
     std::vector<ChunkDesc> chunks;
     std::vector<float> dhi, dlo;
     build_chunks(wave, (int)npix, lam_ref, chunks, dhi, dlo);
+    std::vector<PairF> ph, pl;
+    build_pair_table(chunks, dhi, ph);
+    build_pair_table(chunks, dlo, pl);
     std::vector<float> tau(npix, 0.0f);
+    if (kind_out) kind_out[0] = kind_out[1] = kind_out[2] = kind_out[3] = 0;
     for (size_t c = 0; c < chunks.size(); ++c) {
         const ChunkDesc &cd = chunks[c];
-        // the kernel evaluates the far-field polynomial first, then the wing-only lines, then the mixed ones
-        F2 C2[(FF_DEG + 1) / 2] = {};
-        int nf = 0;
-        for (int pass = 0; pass <= 2; ++pass) {
-            for (int t = 0; t < nlines; ++t) {
-                const double *l = lines + 6 * t;
-                const Line64 L64 = line_setup64(l[0], l[1], l[2], l[3], l[4], l[5], lam_ref);
-                const LineP L = line_pack_full(L64);
-                const double U = L64.A * (cd.rho_s - L64.rc);
-                float Uh, Ul;
-                split2(U, Uh, Ul);
-                const int cls = chunk_class(L.A_hi, Uh, cd.ds, L.c1, (float)eps_cull, (float)eps_far);
-                if (cls_out && pass == 0) cls_out[c * nlines + t] = cls;
-                if (pass == 0) {
-                    if (cls == 3) { farfield_accumulate(L.A_hi, Uh, cd.ds, L.c1, L.a2, C2); ++nf; }
-                    continue;
-                }
-                if (cls != pass) continue;
-                // both classes: direct wing form with s clamped at S_CUT; class 2 then replaces the
-                // clamped value by the core form where s < S_CUT (as the kernel's core pass does)
-                const float c1w = wing_tau(L.c1, S_CUT);
-                for (int i = cd.start; i < cd.start + cd.len; ++i) {
-                    const float u = fma32(L.A_hi, dhi[i], Uh);
-                    const float s = fma32(u, u, L.a2);
-                    tau[i] += wing_tau(L.c1, fmaxf(s, S_CUT));
-                    if (cls == 2 && s < S_CUT) {
-                        float h;
-                        if (L.kappa <= KAPPA_LEAN) {
-                            const float uc = u + fma32(L.A_hi, dlo[i], fma32(L.A_lo, dhi[i], Ul));
-                            h = core_h32_lean(L.a, L.a2, uc);
-                        } else {
-                            float uh, ul;
-                            core_u2(L.A_hi, L.A_lo, dhi[i], dlo[i], Uh, Ul, uh, ul);
-                            h = core_h32(L.a, L.a2, uh, ul);
-                        }
-                        tau[i] += fma32(L.kappa, h, -c1w);
-                    }
-                }
+        // registers of the warp: tau[j][lane] as pairs
+        F2 T[4][32], D[4][32], DL[4][32];
+        for (int j = 0; j < 4; ++j)
+            for (int l = 0; l < 32; ++l) {
+                const PairF v = ph[cd.start + 64 * j + l], w = pl[cd.start + 64 * j + l];
+                D[j][l] = f2(v.x, v.y);
+                DL[j][l] = f2(w.x, w.y);
+                T[j][l] = f2(0.0f);
             }
-            if (pass == 0 && nf) {
-                float C[FF_DEG + 1];
-                for (int m = 0; m < (FF_DEG + 1) / 2; ++m) { C[2 * m] = C2[m].x; C[2 * m + 1] = C2[m].y; }
-                for (int i = cd.start; i < cd.start + cd.len; ++i) tau[i] = farfield_eval(C, dhi[i] * cd.inv_ds);
+        // far lines
+        F2 C2[(FF_DEG + 1) / 2] = {};
+        std::vector<int> cls(nlines);
+        std::vector<LineP> lp(nlines);
+        std::vector<Line64> l64(nlines);
+        for (int t = 0; t < nlines; ++t) {
+            const double *l = lines + 6 * t;
+            l64[t] = line_setup64(l[0], l[1], l[2], l[3], l[4], l[5], lam_ref);
+            lp[t] = line_pack_full(l64[t]);
+            const float Uh = (float)(l64[t].A * (cd.rho_s - l64[t].rc));
+            cls[t] = chunk_class(lp[t].A_hi, Uh, cd.ds, lp[t].c1, lp[t].ucm, (float)eps_cull, (float)eps_far);
+            if (cls_out) cls_out[c * nlines + t] = cls[t];
+            if (cls[t] == 3) farfield_accumulate(lp[t].A_hi, Uh, cd.ds, lp[t].c1, lp[t].a2, C2);
+        }
+        {
+            float C[FF_DEG + 1];
+            for (int m = 0; m < (FF_DEG + 1) / 2; ++m) { C[2 * m] = C2[m].x; C[2 * m + 1] = C2[m].y; }
+            for (int j = 0; j < 4; ++j)
+                for (int l = 0; l < 32; ++l)
+                    T[j][l] = f2(farfield_eval(C, D[j][l].x * cd.inv_ds), farfield_eval(C, D[j][l].y * cd.inv_ds));
+        }
+        for (int t = 0; t < nlines; ++t) {
+            if (cls[t] != 1 && cls[t] != 2) continue;
+            const LineP &L = lp[t];
+            float Uh, Ul;
+            split2(l64[t].A * (cd.rho_s - l64[t].rc), Uh, Ul);
+            if (cls[t] == 1 && kind_out) kind_out[3] += 1;
+            for (int j = 0; j < 4; ++j) {
+                F2 u[32], s[32];
+                bool all_wing = true, all_tab = true;
+                for (int l = 0; l < 32; ++l) {
+                    u[l] = fma2(f2(L.A_hi), D[j][l], f2(Uh));
+                    s[l] = fma2(u[l], u[l], f2(L.a2));
+                    all_wing = all_wing && (s[l].x >= L.scut && s[l].y >= L.scut);
+                    all_tab = all_tab && (fabsf(u[l].x) <= U_TAB && fabsf(u[l].y) <= U_TAB);
+                }
+                const int kind = cls[t] == 1 ? PAIR_WING : pair_kind(all_wing, all_tab);
+                if (cls[t] == 2 && kind_out) kind_out[kind] += 1;
+                for (int l = 0; l < 32; ++l)
+                    T[j][l] = mixed_pair_tau(kind, T[j][l], L, u[l], s[l], D[j][l], DL[j][l], Uh, Ul);
             }
         }
+        for (int j = 0; j < 4; ++j)
+            for (int l = 0; l < 32; ++l) {
+                const int k = 64 * j + l;
+                if (k < cd.len) tau[cd.start + k] = T[j][l].x;
+                if (k + 32 < cd.len) tau[cd.start + k + 32] = T[j][l].y;
+            }
     }
     for (long i = 0; i < npix; ++i) tau_out[i] = (double)tau[i];
 }

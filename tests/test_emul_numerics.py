@@ -79,13 +79,16 @@ def test_kernel_algorithm_on_host_vs_oracle(emul, tag, far_eps, golden):
     with np.errstate(all="ignore"):
         w = 1.0 / o.obj_noise ** 2
     seen = set()
+    kinds_seen = np.zeros(4, dtype=np.int64)
     for p in P:
         lines = _lines(o, p)
         tau = np.empty(wave.size)
         cls = np.zeros(emul.emul_num_chunks(ctypes.c_long(wave.size), wave.ctypes.data_as(dp)) * max(len(lines), 1), dtype=np.int32)
+        kinds = np.zeros(4, dtype=np.int64)
         emul.emul_tau(ctypes.c_long(wave.size), wave.ctypes.data_as(dp), len(lines), lines.ctypes.data_as(dp),
                       ctypes.c_double(0.0), ctypes.c_double(far_eps), tau.ctypes.data_as(dp),
-                      cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int)))
+                      cls.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), kinds.ctypes.data_as(ctypes.POINTER(ctypes.c_long)))
+        kinds_seen += kinds
         assert set(np.unique(cls)) <= ({1, 2, 3} if far_eps else {1, 2})     # nothing culled at cull_eps = 0
         seen |= set(np.unique(cls))
         res, cont, _ = o.unpack(p)
@@ -101,3 +104,37 @@ def test_kernel_algorithm_on_host_vs_oracle(emul, tag, far_eps, golden):
         assert abs((const - 0.5 * chi2) - ref_logl) <= 1e-6 * max(abs(ref_logl), abs(const))
     if far_eps and tag in ("cfg3", "cfg4"):
         assert 3 in seen          # the far-field form is actually exercised
+    if tag in ("cfg2", "cfg3", "cfg4"):
+        assert kinds_seen[0] > 0 and kinds_seen[1] > 0      # row pairs taken as wing and as core inside mixed chunks
+    if tag in ("cfg3", "cfg4"):
+        assert kinds_seen[2] > 0                            # ... and pairs straddling table end and core boundary (small b)
+
+
+@pytest.mark.parametrize("kappa,a0", [(0.01, 1e-4), (0.3, 1.5e-4), (1.0, 3e-4), (8.0, 6e-4), (30.0, 6.5e-4), (200.0, 1e-3)])
+def test_weak_line_forms_vs_wofz(emul, kappa, a0):
+    """The per-line core boundary (line_cut) and the two forms either side of it: the optical-depth error
+    kappa * |H_fp32 - H_wofz| of a line stays below 6e-8 + 3e-7 tau everywhere (flux error F dtau < 1.2e-7)."""
+    scut = ctypes.c_double()
+    emul.emul_line_cut.restype = ctypes.c_int
+    wide = emul.emul_line_cut(ctypes.c_double(kappa), ctypes.c_double(a0), ctypes.byref(scut))
+    assert 16.0 <= scut.value <= 36.0
+    if not wide:
+        assert scut.value == 36.0
+        return
+    assert scut.value < 35.5 and kappa * np.exp(-scut.value) <= 2.6e-8
+    rng = np.random.default_rng(3)
+    u = np.concatenate([rng.uniform(-9, 9, 300000), rng.uniform(-400, 400, 50000)]).astype(np.float32).astype(float)
+    a = np.full_like(u, np.float32(a0))
+    ref = wofz(u + 1j * a).real
+    arrs = [np.ascontiguousarray(a), np.ascontiguousarray(u)]
+    got = np.empty_like(u)
+    emul.emul_voigt_h32_weak(ctypes.c_long(u.size), arrs[0].ctypes.data_as(dp), arrs[1].ctypes.data_as(dp),
+                             ctypes.c_double(scut.value), got.ctypes.data_as(dp))
+    dtau = kappa * np.abs(got - ref)
+    tau = kappa * ref
+    if kappa <= 8.0:
+        assert (dtau <= 6e-8 + 3e-7 * tau).all(), (dtau - 3e-7 * tau).max()
+        assert (np.exp(-tau) * dtau).max() < 1.2e-7
+    else:       # strong lines take the two-float core form in the kernel; here only the wing side is theirs
+        wing = u * u + a * a >= scut.value
+        assert (dtau[wing] <= 6e-8).all()

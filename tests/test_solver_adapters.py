@@ -56,6 +56,33 @@ def test_pool_batches_likelihood_calls():
     assert pool.map(f.lnlhood_dy, []) == []
 
 
+def test_pool_unwraps_nested_wrappers():
+    import functools
+    f = FakeFitter()
+    pool = BatchPool(f)
+    pts = [np.ones(3) * k for k in range(4)]
+
+    class DynestyLike:                      # dynesty's _function_wrapper keeps the callable in .func plus args/kwargs
+        def __init__(self, func):
+            self.func, self.args, self.kwargs = func, (), {}
+
+        def __call__(self, x):
+            return self.func(x, *self.args, **self.kwargs)
+
+    @functools.wraps(f.lnlhood_dy)
+    def wrapped(x):
+        return f.lnlhood_dy(x)
+
+    for fn in (DynestyLike(Wrapper(f.lnlhood_dy)), functools.partial(f.lnlhood_dy), wrapped, DynestyLike(f._scale_cube_pc)):
+        f.batches.clear()
+        pool.map(fn, pts)
+        assert f.batches == [4], fn           # one batched launch, not four scalar calls
+    # a method of our fitter that has no batched form: served point by point, and counted
+    f.batches.clear()
+    pool.map(f.lnlhood_worker.__self__.prior_transform_batch, [pts[0][None, :]])
+    assert pool.scalar_fallbacks == 1
+
+
 def test_pool_falls_back_for_foreign_functions():
     f = FakeFitter()
     pool = BatchPool(f)
