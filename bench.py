@@ -44,9 +44,10 @@ WORKLOAD = "cfg4: 8192 px x 20 comps x 2 lines (CIV doublet), free specres+conti
 # MUFU = 1); derivation in DESIGN.md section 5
 FLOP_PAIR_CLASS = 18     # chunk_class per (line, chunk) pair
 FLOP_PAIR_FAR = 74       # farfield_accumulate per far pair (8 coefficients x 3 series)
-FLOP_NEAR_EVAL = 17      # direct wing form per (line, pixel) of a near (wing or mixed) pair
-FLOP_CORE_LEAN = 38      # extra per line-core pixel, weak line
-FLOP_CORE_PRECISE = 75   # extra per line-core pixel, strong line (two-float coordinate, polynomial exp)
+FLOP_NEAR_EVAL = 14      # direct wing form per (line, pixel): u, s (4), Horner with pre-scaled coefficients (8), accumulate (2); rcp not counted
+FLOP_MIXED_VOTE = 4      # u and s of every pixel of a mixed (line, chunk) pair before the row pair's vote
+FLOP_CORE_LEAN = 45      # per pixel evaluated with the short core form (coordinate fix-up 6, H1 cubic 6, Gaussian factors 10, table index 7, combine 8, kappa 1, accumulate 1, u/s shared)
+FLOP_CORE_PRECISE = 85   # per pixel with the two-float form (two-float coordinate and u^2, polynomial exp)
 FLOP_CHUNK = 64          # summing the slots' far-field partials, per (sample, chunk)
 FLOP_PIXEL = 48          # far-field polynomial (15) + depth32 (23) + residual / chi-square (10); stencil: 2 per padded tap
 CHUNK = 256
@@ -186,7 +187,86 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------
+def make_cfg_fitter(cfg, device):
+    import mcalf_b200
+    from mcalf_b200.workloads import config_kwargs
+    spec, kw = config_kwargs(cfg, GOLDEN)
+    return mcalf_b200.als_fitter(spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                                 **{k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items()
+                                    if k not in ("fitrange", "fitlines", "ncomp")}, device=device)
+
+
+def device_rate(g, U_dev, steps, warmup=2):
+    """logL/s with the parameter block resident in HBM: CUDA events on the launching (current torch) stream."""
+    import torch
+    for _ in range(warmup):
+        g.lnlhood_batch(U_dev, unit_cube=True)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        g.lnlhood_batch(U_dev, unit_cube=True)
+    e1.record()
+    torch.cuda.synchronize()
+    return U_dev.shape[0] * steps / (e0.elapsed_time(e1) * 1e-3)
+
+
+def host_rate(g, U_np, out_np, steps, warmup=1):
+    """logL/s through the C-ABI with HOST buffers (H2D of the parameters and D2H of logL inside the call)."""
+    from mcalf_b200 import capi
+    B = U_np.shape[0]
+
+    def call():
+        capi.check(g._lib.mcalf_loglike_batch(g._ctx, capi.ptr(U_np), B, g.ndim, capi.F_UNIT_CUBE, None, capi.ptr(out_np), None))
+
+    for _ in range(warmup):
+        call()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    return B * steps / (time.perf_counter() - t0)
+
+
+def far_fraction(g, U_dev):
+    g.set_option("collect_stats", 1)
+    g.reset_stats()
+    g.lnlhood_batch(U_dev, unit_cube=True)
+    st = g.stats()
+    g.set_option("collect_stats", 0)
+    return st["evals_far"] / max(st["evals_total"], 1), st
+
+
+def run_sweep(g4, local):
+    """The rest of the BASELINE sweep, measured in the driver-run line: cfg 4 at every batch size,
+    device-resident and end to end (pinned and pageable host buffers), and one line each for cfg 1-3."""
+    import torch
+    out = {"cfg4": [], "configs": []}
+    for B in (4096, 16384, 65536, 262144):
+        Uh = torch.from_numpy(unit_cube(B, g4.ndim, 0)).pin_memory()
+        Oh = torch.empty(B, dtype=torch.float64).pin_memory()
+        Ud = Uh.cuda()
+        steps = max(3, min(40, (1 << 20) // B))
+        rec = {"batch": B, "device": device_rate(g4, Ud, steps), "e2e_pinned": host_rate(g4, Uh.numpy(), Oh.numpy(), steps)}
+        Up = np.array(Uh.numpy())                       # pageable copies: what a CPU sampler hands over
+        rec["e2e_pageable"] = host_rate(g4, Up, np.empty(B), steps)
+        out["cfg4"].append(rec)
+    for cfg, B in ((1, 65536), (2, 65536), (3, 65536)):
+        g = make_cfg_fitter(cfg, local)
+        Uh = torch.from_numpy(np.random.default_rng(4000 + cfg).random((B, g.ndim))).pin_memory()
+        Oh = torch.empty(B, dtype=torch.float64).pin_memory()
+        Ud = Uh.cuda()
+        ff, st = far_fraction(g, Ud)
+        geo = g.geometry()
+        out["configs"].append({"cfg": cfg, "batch": B, "npix": geo["npix"], "ndim": g.ndim, "device": device_rate(g, Ud, 6),
+                               "e2e_pinned": host_rate(g, Uh.numpy(), Oh.numpy(), 4), "frac_far": ff,
+                               "evals_per_logL": st["evals_total"] / B, "cta_threads": geo["threads"], "ctas_per_sm": geo["ctas_per_sm"]})
+        g.close()
+    out["unit"] = UNIT
+    return out
+
+
 def run_ours(args):
+    import hashlib
     import torch
     import torch.distributed as dist
 
@@ -245,7 +325,6 @@ def run_ours(args):
     # ---- end to end through the host-buffer API ----
     out_host = torch.empty(B, dtype=torch.float64).pin_memory()
     Uh, Oh = U_host.numpy(), out_host.numpy()
-    import ctypes
     from mcalf_b200 import capi
 
     def step_host():
@@ -269,6 +348,43 @@ def run_ours(args):
     ms = float(ms.item())
     e2e_s = float(e2e_s.item())
 
+    # ---- strong scaling (BASELINE config 5): ONE global batch, identical on every rank, sharded by sample
+    # through the product's own distributed.ShardedLikelihood; the gathered logL vector must be bit-identical
+    # to the same batch evaluated on a single GPU (rank 0 checks) ----
+    strong = []
+    if not args.no_strong:
+        from mcalf_b200.distributed import ShardedLikelihood
+        sl = ShardedLikelihood(g, gather=args.gather) if world > 1 else None
+        for Bg in (16384, 262144):
+            Ug = torch.from_numpy(unit_cube(Bg, g.ndim, 0)).cuda()      # the same seed on every rank
+            single = g.lnlhood_batch(Ug, unit_cube=True).clone()       # this GPU alone, the whole batch
+            steps = 20 if Bg <= 65536 else max(3, min(K, 10))
+
+            def sstep():
+                return sl.lnlhood_batch(Ug, unit_cube=True) if sl is not None else g.lnlhood_batch(Ug, unit_cube=True)
+
+            for _ in range(3):
+                full = sstep()
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(steps):
+                full = sstep()
+            s1.record()
+            barrier()
+            sms = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device="cuda")
+            same = torch.tensor([1.0 if torch.equal(full, single) else 0.0], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(sms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            digest = hashlib.sha256(full.cpu().numpy().tobytes()).hexdigest()[:16]
+            strong.append({"global_batch": Bg, "batch_per_gpu": -(-Bg // world), "value": Bg * steps / (float(sms.item()) * 1e-3),
+                           "ms_per_step": float(sms.item()) / steps, "steps": steps,
+                           "global_checksum": digest, "sum": float(full.sum().item()),
+                           "bit_identical_to_single_gpu": bool(same.item() == 1.0),
+                           "gather": (sl.gather_used if sl is not None else "none")})
+            assert same.item() == 1.0, "sharded result differs from the single-GPU result (global batch %d)" % Bg
+
     if rank == 0:
         # ---- roofline of the fused kernel: measured live, kernel alone on the stream ----
         g.set_option("collect_stats", 1)
@@ -286,14 +402,7 @@ def run_ours(args):
         P = g.prior_transform_batch(U_dev).cpu().numpy()
         sig = P[:, 0] / 2.354820 / g.velstep
         n = np.where(P[:, 0] > g.velstep, np.ceil(3.0348 * sig), 0)
-        taps_padded = 2 * (4 * np.ceil(n / 4)) + 4
         npix = g.obj_wl.size
-        near = st["evals_wing"] + st["evals_mixed"]
-        pairs = st["evals_total"] / CHUNK
-        flop = (FLOP_PAIR_CLASS * pairs + FLOP_PAIR_FAR * st["evals_far"] / CHUNK + FLOP_NEAR_EVAL * near
-                + FLOP_CORE_LEAN * (st["evals_core"] - st["evals_core_precise"])
-                + FLOP_CORE_PRECISE * st["evals_core_precise"] + FLOP_CHUNK * geo["nchunks"] * B
-                + npix * (FLOP_PIXEL * B + 2.0 * taps_padded.sum()))
         f_core_canon = 2.0 * math.sqrt(111.0) * np.mean(P[:, 5::3][:, :20]) / g.velstep / npix   # SURVEY 8d estimate
         canon = (st["evals_total"] * (CANON_EVAL + f_core_canon * CANON_CORE + (1 - f_core_canon) * CANON_WING)
                  + npix * (8.0 * B + 2.0 * (2 * n + 1).sum()))
@@ -304,8 +413,19 @@ def run_ours(args):
         except (OSError, ValueError):
             sm_max = 1965.0
         peak_nominal = geo["sm_count"] * 128 * 2 * sm_max * 1e6 / 1e12
-        achieved = flop / (kernel_ms * 1e-3) / 1e12
-        traffic, ncu = None, None
+        # executed FP32 flops per logL: (i) the per-path model (op counts read off the source x the kernel's own
+        # path counters of THIS run), (ii) the count derived from the committed ncu opcode histogram of the same
+        # command (profiles/ncu_opcodes_r02.json: per-instruction thread counts incl. the packed FFMA2 forms)
+        flop_model = model_flops(st, geo, B, npix, n)
+        counters, traffic = None, None
+        try:
+            cj = json.load(open(os.path.join(ROOT, "profiles", "ncu_opcodes_r02.json")))
+            if cj.get("samples_per_launch") == B:
+                counters = {k: cj[k] for k in ("fp32_flop_per_logL", "warp_instructions_per_logL", "fma_pipe_issue_cycles_per_logL",
+                                               "fp32_arith_share_of_warp_instructions", "source") if k in cj}
+        except (OSError, ValueError, KeyError):
+            pass
+        ncu = None
         try:   # dram__bytes_read + dram__bytes_write of this kernel at this batch size, from the committed ncu capture
             tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
             if tr.get("batch") == B:
@@ -314,12 +434,18 @@ def run_ours(args):
                                       "warp_instructions_per_logL", "source") if k in tr}
         except (OSError, ValueError, KeyError):
             pass
+        flop_per_logl = counters["fp32_flop_per_logL"] if counters else flop_model / B
+        achieved = flop_per_logl * B / (kernel_ms * 1e-3) / 1e12
         roofline = {
             "bound": "fp32_alu", "achieved": achieved, "peak": peak_meas, "unit": "TFLOP/s", "frac": achieved / peak_meas,
             "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram read+write; algorithmic: %d)" % (B * (g.ndim * 8 + 8)),
             "peak_source": "FFMA-only microbenchmark in this run (MEASURED_PEAKS.json has no FP32 entry)",
             "peak_nominal": peak_nominal, "frac_of_nominal": achieved / peak_nominal,
-            "kernel": "mcalf_fast_kernel", "kernel_ms": kernel_ms, "flop_per_logL": flop / B,
+            "kernel": "mcalf_fast_kernel", "kernel_ms": kernel_ms, "flop_per_logL": flop_per_logl,
+            "flop_source": ("ncu opcode histogram (committed capture of this command) x this run's kernel time" if counters
+                            else "per-path model x this run's path counters"),
+            "flop_per_logL_model": flop_model / B, "flop_per_logL_counters": counters["fp32_flop_per_logL"] if counters else None,
+            "counters": counters,
             "evals_per_logL": st["evals_total"] / B, "frac_wing": st["evals_wing"] / st["evals_total"],
             "frac_mixed": st["evals_mixed"] / st["evals_total"], "frac_core": st["evals_core"] / st["evals_total"],
             "frac_far": st["evals_far"] / st["evals_total"],
@@ -328,6 +454,7 @@ def run_ours(args):
             "hbm_bytes_per_logL": g.ndim * 8 + 8,
             "ncu": ncu,     # from the committed capture under profiles/ (not measured in this run)
         }
+        sweep = run_sweep(g, local) if (world == 1 and not args.no_sweep) else None
         # ---- CPU baseline: oracle port on the host cores, bounded sample of the same vectors ----
         cpu = None
         if cpu_workers is not None:
@@ -352,11 +479,24 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "strong": strong,
+            "sweep": sweep,
         }
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def model_flops(st, geo, B, npix, n):
+    """Executed FP32 flops of one launch from the kernel's own path counters (FMA = 2, add/mul = 1; FFMA2 = 4)."""
+    taps_padded = 2 * (4 * np.ceil(n / 4)) + 4
+    pairs = st["evals_total"] / CHUNK
+    near_evals = st["evals_wing"] + st["evals_mixed"] - st["evals_core"] + st["evals_core_straddle"]
+    lean = st["evals_core"] - st["evals_core_precise"]
+    return (FLOP_PAIR_CLASS * pairs + FLOP_PAIR_FAR * st["evals_far"] / CHUNK + FLOP_NEAR_EVAL * near_evals
+            + FLOP_MIXED_VOTE * st["evals_mixed"] + FLOP_CORE_LEAN * lean + FLOP_CORE_PRECISE * st["evals_core_precise"]
+            + FLOP_CHUNK * geo["nchunks"] * B + npix * (FLOP_PIXEL * B + 2.0 * taps_padded.sum()))
 
 
 def emit(line):
@@ -380,6 +520,10 @@ def main():
     ap.add_argument("--batch", type=int, default=262144, help="parameter vectors per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the batch-size / config sweep (profiling runs)")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling (one global batch) records")
+    ap.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer"],
+                    help="logL gather of the sharded path: NCCL all-gather, or the kernel's own peer stores")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

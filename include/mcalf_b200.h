@@ -111,6 +111,18 @@ void mcalf_destroy(mcalf_ctx *ctx);
 int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
                         void *stream, double *logl_out, double *chi2_out);
 
+/*
+ * The sharded form (MPI ranks each owning an als_fitter, cli.py:37-41,156-158, become one process
+ * per GPU each evaluating a contiguous shard of one global batch).  As mcalf_loglike_batch with
+ * MCALF_F_ON_DEVICE, but the kernel stores logL of sample b to logl_peers[p][b] for every p < npeers (<= 8):
+ * the buffers are the ranks' gather buffers -- this GPU's own and the other GPUs' mapped into this device's
+ * address space (CUDA IPC / symmetric memory over NVLink) -- each already offset to where this shard starts.
+ * The logL gather is thus fused into the kernel's tail as peer stores; no collective follows, only the
+ * caller's cross-rank barrier.
+ */
+int mcalf_loglike_batch_peers(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,
+                              void *stream, double *const *logl_peers, int npeers);
+
 /* Model flux for B parameter vectors, [B, npix] row-major: replaces reconstruct_spec (:409-449),
  * reconstruct_onecomp (:379-392) and reconstruct_onecomp_fill (:394-406) via flags. */
 int mcalf_model_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags,

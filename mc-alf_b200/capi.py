@@ -53,6 +53,7 @@ SIGNATURES = {
     "mcalf_create": (_int, [ctypes.POINTER(Problem), _int, ctypes.POINTER(_vp)]),
     "mcalf_destroy": (None, [_vp]),
     "mcalf_loglike_batch": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp]),
+    "mcalf_loglike_batch_peers": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, ctypes.POINTER(_vp), _int]),
     "mcalf_model_batch": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, _vp]),
     "mcalf_prior_transform_batch": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, _vp]),
     "mcalf_voigt_h": (_int, [_int, _int, _vp, _vp, _i64, _vp]),

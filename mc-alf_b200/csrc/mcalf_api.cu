@@ -244,8 +244,11 @@ bool is_pinned(const void *p) {
 // fallback_flag (mapped host memory, nullable): when given, the fp64 fix-up kernel is NOT launched here; the
 // caller synchronises, looks at the flag and calls enqueue_fixup only if a sample was re-routed
 int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long long n, long long ld, uint32_t flags,
-            double *d_logl, double *d_chi2, void *d_flux, int *fallback_flag = nullptr) {
+            double *d_logl, double *d_chi2, void *d_flux, int *fallback_flag = nullptr, double *const *peers = nullptr,
+            int npeers = 0) {
     BatchArgs a{};
+    a.npeers = npeers;
+    for (int p = 0; p < npeers; ++p) a.logl_peer[p] = peers[p];
     a.params = d_params;
     a.B = n;
     a.ld = ld;
@@ -293,7 +296,7 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
 }
 
 int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uint32_t flags, void *stream, double *logl,
-              double *chi2, void *flux) {
+              double *chi2, void *flux, double *const *peers = nullptr, int npeers = 0) {
     if (!c) return fail(MCALF_E_INVALID, "null context");
     if (B < 0) return fail(MCALF_E_INVALID, "negative batch size");
     if (B == 0) return MCALF_OK;
@@ -325,7 +328,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
         }
         c->dev_last_stream = st;
         c->dev_has_last = true;
-        return enqueue(c, s, st, params, B, ld, flags, logl, chi2, flux);
+        return enqueue(c, s, st, params, B, ld, flags, logl, chi2, flux, nullptr, peers, npeers);
     }
 
     // Small calls (the scalar callbacks of a CPU sampler, one live set): the kernel reads the parameters
@@ -676,6 +679,18 @@ int mcalf_loglike_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t
     const uint32_t allowed = MCALF_F_UNIT_CUBE | MCALF_F_ON_DEVICE | MCALF_F_FP64 | MCALF_F_TARGONLY | MCALF_F_NO_TRUNC;
     if (flags & ~allowed) return fail(MCALF_E_INVALID, "flag 0x%x not valid for mcalf_loglike_batch", flags & ~allowed);
     return run_batch(ctx, params, B, ld, flags, stream, logl_out, chi2_out, nullptr);
+}
+
+int mcalf_loglike_batch_peers(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags, void *stream,
+                              double *const *logl_peers, int npeers) {
+    if (npeers < 1 || npeers > MCALF_MAX_PEERS) return fail(MCALF_E_INVALID, "npeers must be in [1, %d]", MCALF_MAX_PEERS);
+    if (!logl_peers) return fail(MCALF_E_INVALID, "null peer list");
+    for (int p = 0; p < npeers; ++p)
+        if (!logl_peers[p]) return fail(MCALF_E_INVALID, "null peer buffer %d", p);
+    const uint32_t allowed = MCALF_F_UNIT_CUBE | MCALF_F_ON_DEVICE | MCALF_F_FP64 | MCALF_F_TARGONLY | MCALF_F_NO_TRUNC;
+    if (flags & ~allowed) return fail(MCALF_E_INVALID, "flag 0x%x not valid for mcalf_loglike_batch_peers", flags & ~allowed);
+    if (!(flags & MCALF_F_ON_DEVICE)) return fail(MCALF_E_INVALID, "mcalf_loglike_batch_peers takes device pointers (MCALF_F_ON_DEVICE)");
+    return run_batch(ctx, params, B, ld, flags, stream, nullptr, nullptr, nullptr, logl_peers, npeers);
 }
 
 int mcalf_model_batch(mcalf_ctx *ctx, const double *params, int64_t B, int64_t ld, uint32_t flags, void *stream, void *flux_out) {

@@ -33,11 +33,16 @@ struct DevProblem {
     const double *blo, *bhi;            // [ndim] prior bounds
 };
 
+constexpr int MCALF_MAX_PEERS = 8;
+
 struct BatchArgs {
     const double *params;
     long long B, ld;
-    uint32_t flags, pad_;
+    uint32_t flags;
+    int npeers;                         // > 0: logL of sample b is ALSO stored to logl_peer[p][b], p < npeers
     double *logl_out, *chi2_out;
+    double *logl_peer[MCALF_MAX_PEERS]; // buffers of other GPUs mapped into this device's address space (NVLink peer
+                                        // stores at the kernel tail: the logL gather of the sharded path, no collective)
     void *flux_out;
     unsigned int *work_counter;         // zero at launch (cleared by the previous launch, see clear_counters)
     unsigned int *fallback_count;       // zero at launch

@@ -26,6 +26,13 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// one sample's results: local buffers, and the peers' gather buffers when the batch is one shard of a global one
+__device__ __forceinline__ void store_results(const BatchArgs &Bt, long long b, double logl, double chi2) {
+    if (Bt.logl_out) Bt.logl_out[b] = logl;
+    if (Bt.chi2_out) Bt.chi2_out[b] = chi2;
+    for (int p = 0; p < Bt.npeers; ++p) Bt.logl_peer[p][b] = logl;       // st.global on mapped peer memory (NVLink)
+}
+
 __device__ __forceinline__ int warp_sum_int(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -497,8 +504,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (lane == 0) {
                 double logl = P.logC - 0.5 * v;
                 if (P.asymmlike && ((double)c5 > P.asym_t5 || (double)c4 > P.asym_t4)) logl = -INFINITY;   // :296-303
-                if (Bt.logl_out) Bt.logl_out[b] = logl;
-                if (Bt.chi2_out) Bt.chi2_out[b] = v + P.chi2_add;
+                store_results(Bt, b, logl, v + P.chi2_add);
             }
         }
     }
@@ -623,8 +629,7 @@ mcalf_fp64_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (lane == 0) {
                 double logl = P.logC - 0.5 * v;
                 if (P.asymmlike && ((double)c5 > P.asym_t5 || (double)c4 > P.asym_t4)) logl = -INFINITY;
-                if (Bt.logl_out) Bt.logl_out[b] = logl;
-                if (Bt.chi2_out) Bt.chi2_out[b] = v + P.chi2_add;
+                store_results(Bt, b, logl, v + P.chi2_add);
             }
         }
     }
