@@ -378,6 +378,20 @@ class als_fitter:
                                                      capi.ptr(chi)))
         return (out, chi) if return_chi2 else out
 
+    def lnlhood_batch_peers(self, P, peer_ptrs, unit_cube=False, fp64=None, no_trunc=False):
+        """The sharded form: logL of every row of the CUDA tensor ``P`` (one shard of a global batch) is stored
+        by the kernel itself to every address in ``peer_ptrs`` (+ 8 bytes per row) -- the ranks' gather buffers,
+        this GPU's and the others' mapped over NVLink (``mcalf_b200.distributed``).  Enqueues on the current
+        torch stream; no collective is involved."""
+        rows, B, ld, on_dev = self._rows(P, self.ndim)
+        if not on_dev:
+            raise ValueError("lnlhood_batch_peers takes a CUDA tensor")
+        if not 1 <= len(peer_ptrs) <= 8:
+            raise ValueError("1 to 8 peer buffers")
+        arr = (ctypes.c_void_p * len(peer_ptrs))(*[int(p) for p in peer_ptrs])
+        flags = self._flags(unit_cube, fp64, no_trunc=no_trunc) | capi.F_ON_DEVICE
+        capi.check(self._lib.mcalf_loglike_batch_peers(self._ctx, capi.ptr(rows), B, ld, flags, self._stream(), arr, len(peer_ptrs)))
+
     def chi2_batch(self, P, unit_cube=False, fp64=None):
         return self.lnlhood_batch(P, unit_cube=unit_cube, fp64=fp64, return_chi2=True)[1]
 

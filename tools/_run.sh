@@ -1,3 +1,7 @@
-python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x > gpurun_out/tests_r02c.log 2>&1; tail -3 gpurun_out/tests_r02c.log
-python bench.py --no-cpu --no-sweep --no-strong > gpurun_out/bench_r02c.json 2> gpurun_out/bench_r02c.err; head -c 400 gpurun_out/bench_r02c.json; echo
-python tools/exp_geometry.py 4 2 > gpurun_out/geom_r02c.log 2>&1; cat gpurun_out/geom_r02c.log
+nvidia-smi -L
+python -m pytest tests/test_gpu_multirank.py -q -s -m gpu -p no:cacheprovider > gpurun_out/mr_r02d.log 2>&1; tail -15 gpurun_out/mr_r02d.log
+for mode in auto nccl; do
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --gather $mode > gpurun_out/bench2_$mode.json 2> gpurun_out/bench2_$mode.err
+echo "exit $?"; tail -3 gpurun_out/bench2_$mode.err; python -c "
+import json; d=json.load(open('gpurun_out/bench2_$mode.json')); print(d['value'], d['e2e']['value']); [print(s) for s in d['strong']]"
+done
