@@ -91,7 +91,8 @@ typedef struct mcalf_stats {
     uint64_t evals_far;        /* ... in pairs folded into the chunk's far-field polynomial             */
     uint64_t evals_core_precise; /* ... of the core ones that took the two-float form (kappa > 8)          */
     uint64_t evals_core_straddle; /* ... of the core ones in row pairs that also needed the wing form (per-pixel select) */
-    double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events)            */
+    double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events): device-pointer and small
+                                  host calls always, pipelined host slices only while collect_stats is on */
 } mcalf_stats_t;
 
 /* Build a context on CUDA device `device` (replaces als_fitter.__init__ state, :65-200). */
@@ -147,7 +148,8 @@ int mcalf_reset_stats(mcalf_ctx *ctx);
  *                      chunk's far-field expansion of the Lorentzian wings (default 1e-9; 0 = never);
  *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default 0.01,
  *                      upper limit 0.02: the validity range of the fp32 line-core series);
- *          "collect_stats" 0/1; "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);
+ *          "collect_stats" 0/1; "check_selftest" 0/1 (checked build only: the next launches report a violation on purpose);
+ *          "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);
  *          "ctas_per_sm" persistent CTAs per SM (0 = what the occupancy calculator allows);
  *          "dense" 1/0/-1: force / forbid / choose automatically the 48-register build of the fp32 kernel
  *                  (CTAs of <= 256 threads; used when it seats more CTAs per SM);
@@ -168,6 +170,9 @@ int mcalf_host_free(void *ptr);
 
 const char *mcalf_last_error(void);
 int mcalf_abi_version(void);
+/* 1 for libmcalf_b200_check.so (-DMCALF_CHECK: every index the fp32 kernel forms is validated on the device and a
+ * violation makes the batch call fail with MCALF_E_CUDA), 0 for the product library. */
+int mcalf_is_checked_build(void);
 
 #ifdef __cplusplus
 }

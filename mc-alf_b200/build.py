@@ -6,6 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmcalf_b200.so")
+CHECK_LIB = os.path.join(HERE, "libmcalf_b200_check.so")
 SOURCES = ["mcalf_kernels.cu", "mcalf_api.cu"]
 HEADERS = ["mcalf_device.h", "host_setup.h", "voigt_math.cuh", "voigt_tables.inc", os.path.join("..", "..", "include", "mcalf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
@@ -19,25 +20,28 @@ def nvcc_path():
     raise RuntimeError("nvcc not found: libmcalf_b200.so cannot be built")
 
 
-def stale():
-    if not os.path.exists(LIB):
+def stale(lib=LIB):
+    if not os.path.exists(lib):
         return True
-    t = os.path.getmtime(LIB)
+    t = os.path.getmtime(lib)
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
-def build(force=False, verbose=False):
-    """Compile the CUDA kernels and the C-ABI into mc-alf_b200/libmcalf_b200.so; returns its path."""
-    if not force and not stale():
-        return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+def build(force=False, verbose=False, checked=False):
+    """Compile the CUDA kernels and the C-ABI into mc-alf_b200/libmcalf_b200.so (``checked``: the bounds-
+    asserting -DMCALF_CHECK variant libmcalf_b200_check.so, test infrastructure); returns its path."""
+    lib = CHECK_LIB if checked else LIB
+    if not force and not stale(lib):
+        return lib
+    cmd = [nvcc_path()] + NVCC_FLAGS + (["-DMCALF_CHECK"] if checked else []) + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build(force=True, checked=True))

@@ -7,6 +7,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libmcalf_b200.so")
+CHECK_LIB_PATH = os.path.join(HERE, "libmcalf_b200_check.so")      # -DMCALF_CHECK build (bounds-asserting kernels)
 
 ABI_VERSION = 2
 OK, E_INVALID, E_CUDA, E_NODEVICE, E_RESOURCE = 0, -1, -2, -3, -4
@@ -50,6 +51,7 @@ _vp, _i64, _u32, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, ctypes
 SIGNATURES = {
     "mcalf_abi_version": (_int, []),
     "mcalf_last_error": (ctypes.c_char_p, []),
+    "mcalf_is_checked_build": (_int, []),
     "mcalf_create": (_int, [ctypes.POINTER(Problem), _int, ctypes.POINTER(_vp)]),
     "mcalf_destroy": (None, [_vp]),
     "mcalf_loglike_batch": (_int, [_vp, _vp, _i64, _i64, _u32, _vp, _vp, _vp]),
@@ -81,10 +83,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = CHECK_LIB_PATH if os.environ.get("MCALF_B200_CHECK") == "1" else LIB_PATH
+    if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -m mcalf_b200.build` (nvcc, sm_100a). "
-                          "There is no CPU fallback." % LIB_PATH)
-    lib = ctypes.CDLL(LIB_PATH)
+                          "There is no CPU fallback." % path)
+    lib = ctypes.CDLL(path)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)   # AttributeError if the library lacks a declared symbol
         fn.restype = res

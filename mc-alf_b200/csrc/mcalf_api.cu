@@ -112,7 +112,25 @@ struct mcalf_ctx {
     cudaStream_t util_stream = nullptr;
     double *util_dev = nullptr;
     size_t util_cap = 0;
+    // samplers hand over the same buffers call after call: the (slow, driver-locked) pointer query is remembered
+    struct PinEntry { const void *p = nullptr; bool pinned = false; } pin_cache[8];
+    int pin_next = 0;
+    bool is_pinned(const void *p);
 };
+
+namespace {
+bool query_pinned(const void *p);
+}
+bool mcalf_ctx::is_pinned(const void *p) {
+    if (!p) return false;
+    for (const PinEntry &e : pin_cache)
+        if (e.p == p) return e.pinned;
+    PinEntry &slot = pin_cache[pin_next];
+    pin_next = (pin_next + 1) % 8;
+    slot.p = p;
+    slot.pinned = query_pinned(p);
+    return slot.pinned;
+}
 
 namespace {
 struct BusyGuard {
@@ -146,14 +164,14 @@ int choose_launch(mcalf_ctx *c) {
     if (nwarps > 32) nwarps = 32;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, c->device));
-    size_t smem = fast_smem_bytes(P, nwarps);
+    c->P.lay = fast_smem_layout(P);
+    size_t smem = (size_t)c->P.lay.bytes;
     size_t static_smem = 0;            // the kernel's fixed-address H1 table
     // (also raises every kernel's dynamic shared-memory limit to what the device allows: the attribute is
     // held per function and device, not per context, so it is never set to one problem's size)
     CU(configure_kernels((size_t)prop.sharedMemPerBlockOptin, &static_smem));
     while (smem + static_smem > (size_t)prop.sharedMemPerBlockOptin && nwarps > 1) {
         nwarps = (nwarps + 1) / 2;
-        smem = fast_smem_bytes(P, nwarps);
     }
     if (smem + static_smem > (size_t)prop.sharedMemPerBlockOptin)
         return fail(MCALF_E_RESOURCE, "problem needs %zu B of shared memory per CTA (limit %zu): too many pixels/lines", smem,
@@ -230,7 +248,7 @@ int ensure_slot(mcalf_ctx *c, Slot &s, long long n, long long ld, size_t flux_by
 }
 
 // true when `p` is page-locked host memory the copy engines can reach directly
-bool is_pinned(const void *p) {
+bool query_pinned(const void *p) {
     if (!p) return false;
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -264,7 +282,8 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
     a.fallback_list = s.fallback;
     a.fallback_flag = fallback_flag;
     a.stats = c->collect_stats ? c->d_stats : nullptr;
-    CU(cudaEventRecord(s.k0, st));
+    const bool timed = c->collect_stats || &s == &c->dev_slot || &s == &c->zc_slot;   // last_kernel_ms; the pipelined slices skip the two records
+    if (timed) CU(cudaEventRecord(s.k0, st));
     const int fp64_grid = (int)std::min<long long>(n, (long long)c->sm_count * 8);
     if (flags & MCALF_F_FP64) {
         CU(launch_fp64(c->P, a, nullptr, nullptr, fp64_grid, c->smem_fp64, st));
@@ -290,13 +309,31 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
             s.pending_count = cnt + 1;
         }
     }
-    CU(cudaEventRecord(s.k1, st));
+    if (timed) CU(cudaEventRecord(s.k1, st));
     c->samples += (uint64_t)n;
     return MCALF_OK;
 }
 
+int run_batch_inner(mcalf_ctx *c, const double *params, long long B, long long ld, uint32_t flags, void *stream, double *logl,
+                    double *chi2, void *flux, double *const *peers, int npeers);
+
 int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uint32_t flags, void *stream, double *logl,
               double *chi2, void *flux, double *const *peers = nullptr, int npeers = 0) {
+    const int rc = run_batch_inner(c, params, B, ld, flags, stream, logl, chi2, flux, peers, npeers);
+#if defined(MCALF_CHECK)
+    // bounds-checked build: every batch call ends with a device synchronisation and a look at the violation mask
+    if (rc == MCALF_OK && c) {
+        ON_DEVICE(c->device);
+        unsigned int mask = 0u;
+        CU(check_flag_fetch(&mask));
+        if (mask) return fail(MCALF_E_CUDA, "bounds check failed in the fp32 kernel (mask 0x%x; bits in voigt_math.cuh)", mask);
+    }
+#endif
+    return rc;
+}
+
+int run_batch_inner(mcalf_ctx *c, const double *params, long long B, long long ld, uint32_t flags, void *stream, double *logl,
+                    double *chi2, void *flux, double *const *peers, int npeers) {
     if (!c) return fail(MCALF_E_INVALID, "null context");
     if (B < 0) return fail(MCALF_E_INVALID, "negative batch size");
     if (B == 0) return MCALF_OK;
@@ -363,7 +400,7 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     // kernels back to back; only the first slice's H2D is exposed, and the results come back in one copy.
     if (!flux && B > std::min<long long>(c->slice, 2048)) {
         const long long slice = c->slice;
-        const bool pin_in = is_pinned(params), pin_logl = is_pinned(logl), pin_chi2 = is_pinned(chi2);
+        const bool pin_in = c->is_pinned(params), pin_logl = c->is_pinned(logl), pin_chi2 = c->is_pinned(chi2);
         if (!c->copy_stream) {
             CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
             CU(cudaStreamCreateWithFlags(&c->comp_stream, cudaStreamNonBlocking));
@@ -416,15 +453,15 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
     // H2D of slice k+1 and the D2H of slice k-1 overlap the kernel of slice k
     long long slice = c->slice;
     // pageable input: the staging memcpy runs on this thread, so smaller slices overlap it better with the kernels
-    if (B > 8192 && !is_pinned(params)) slice = std::min<long long>(slice, 8192);
+    if (B > 8192 && !c->is_pinned(params)) slice = std::min<long long>(slice, 8192);
     if (flux) slice = std::max<long long>(1, std::min<long long>(slice, (long long)((64u << 20) / ((size_t)c->P.npix * esize))));
     slice = std::min(slice, B);
     const size_t flux_bytes = flux ? (size_t)slice * c->P.npix * esize : 0;
     // caller buffers that are already page-locked (mcalf_host_alloc, torch pin_memory) skip the staging copy
     // (small calls are always staged: the pointer queries would cost more than the copies)
     const bool small = (size_t)B * (size_t)ld * sizeof(double) <= (64u << 10) && !flux;
-    const bool pin_in = !small && is_pinned(params);
-    const bool pin_logl = !small && is_pinned(logl), pin_chi2 = !small && is_pinned(chi2), pin_flux = !small && is_pinned(flux);
+    const bool pin_in = !small && c->is_pinned(params);
+    const bool pin_logl = !small && c->is_pinned(logl), pin_chi2 = !small && c->is_pinned(chi2), pin_flux = !small && c->is_pinned(flux);
     struct Pending { long long off = 0, n = 0; bool live = false; } pend[NBUF];
     auto drain = [&](int k) -> int {
         Slot &s = c->slot[k];
@@ -476,6 +513,13 @@ int run_batch(mcalf_ctx *c, const double *params, long long B, long long ld, uin
 extern "C" {
 
 int mcalf_abi_version(void) { return MCALF_ABI_VERSION; }
+int mcalf_is_checked_build(void) {
+#if defined(MCALF_CHECK)
+    return 1;
+#else
+    return 0;
+#endif
+}
 const char *mcalf_last_error(void) { return g_err; }
 
 int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
@@ -801,6 +845,7 @@ int mcalf_get_stats(mcalf_ctx *c, mcalf_stats_t *out) {
         float ms = 0.f;
         Slot &s = c->last_slot == NBUF + 1 ? c->zc_slot : c->last_slot == NBUF ? c->dev_slot : (c->last_slot >= 0 ? c->slot[c->last_slot] : c->ring[c->last_ring]);
         if (cudaEventElapsedTime(&ms, s.k0, s.k1) == cudaSuccess) out->last_kernel_ms = ms;
+        else cudaGetLastError();      // pipelined host slices are only timed while collect_stats is on
     }
     return MCALF_OK;
 }
@@ -828,6 +873,8 @@ int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
         c->P.a_max = value;
     } else if (!strcmp(name, "collect_stats")) {
         c->collect_stats = value != 0.0;
+    } else if (!strcmp(name, "check_selftest")) {
+        c->P.check_selftest = value != 0.0;      // only the -DMCALF_CHECK build looks at it
     } else if (!strcmp(name, "threads")) {
         const int t = (int)value;
         if (t < 0 || t > 1024 || (t % 32)) return fail(MCALF_E_INVALID, "threads must be a multiple of 32 in [0, 1024]");

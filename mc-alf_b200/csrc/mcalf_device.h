@@ -9,6 +9,11 @@
 
 namespace mcalf {
 
+// byte offsets of the fp32 kernel's dynamic shared-memory arrays (fast_smem_layout)
+struct SmemLayout {
+    int theta, A64, rc64, lp, uarr, nmask, cmask, farp, taps, flux, red, misc, bytes;
+};
+
 // Everything als_fitter.__init__ leaves behind (hires_fitter.py:65-200), in device form.
 struct DevProblem {
     int npix, npix4, nchunks, nlines;
@@ -16,9 +21,12 @@ struct DevProblem {
     int startind, endind, free_specres, free_cont;
     int asymmlike, halo, nmax, nmax4;
     int Lmax, mwords;                   // mwords: 32-bit words of a per-chunk line mask, ceil(Lmax / 32)
-    int scratch_in_flux, pad2_;          // pass-A outputs of a chunk live in its slice of the depth buffer
+    int scratch_in_flux, check_selftest; // pass-A outputs of a chunk live in its slice of the depth buffer; check_selftest: the
+                                        // -DMCALF_CHECK build raises violation bit 31 on purpose (proves the plumbing)
     int cslot_w, cslot_lw, nslots, vwarps; // lanes per chunk group (power of two), its log2, slots = vwarps * 32 / cslot_w
     float eps_cull, eps_far;
+    SmemLayout lay;
+    int pad3_;
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
@@ -52,7 +60,7 @@ struct BatchArgs {
     unsigned long long *stats;          // nullable: {total, wing, mixed, core, culled, far, core-precise} evaluations
 };
 
-size_t fast_smem_bytes(const DevProblem &P, int nwarps);
+SmemLayout fast_smem_layout(const DevProblem &P);
 size_t fp64_smem_bytes(const DevProblem &P);
 cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes);
 cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm);
@@ -63,5 +71,6 @@ cudaError_t launch_prior(const DevProblem &P, const double *cube, long long B, l
                          cudaStream_t st);
 cudaError_t launch_voigt_h(int mode, const double *u, const double *a, long long n, double *out, cudaStream_t st);
 cudaError_t launch_ffma_peak(float *out, int grid, int threads, int iters, cudaStream_t st);
+cudaError_t check_flag_fetch(unsigned int *mask);   // -DMCALF_CHECK build: synchronise, read and clear the bounds-violation mask
 
 }  // namespace mcalf

@@ -165,23 +165,43 @@ struct FastSmem {
     size_t bytes;
 };
 
-MCALF_HD FastSmem carve(unsigned char *base, const DevProblem &P) {
-    FastSmem s;
+// The byte offsets are computed once on the host (fast_smem_layout, at context creation) and travel in DevProblem:
+// the kernel only adds them to the shared-memory base instead of re-deriving them from the problem sizes.
+static SmemLayout make_layout(const DevProblem &P) {
+    SmemLayout L;
     size_t o = 0;
-    auto take = [&](size_t bytes) { unsigned char *p = base + o; o += (bytes + 15) & ~(size_t)15; return p; };
-    s.theta = (double *)take(sizeof(double) * P.ndim_pad);
-    s.A64 = (double *)take(sizeof(double) * P.Lmax);
-    s.rc64 = (double *)take(sizeof(double) * P.Lmax);
-    s.lp = (LineP *)take(sizeof(LineP) * P.Lmax);
-    s.uarr = (float *)take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * P.Lmax);
-    s.nmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
-    s.cmask = (unsigned *)take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
-    s.farp = (float *)take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
-    s.taps = (float *)take(sizeof(float) * (2 * P.nmax4 + 8));
-    s.flux = (float *)take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
-    s.red = (double *)take(sizeof(double) * 64);
-    s.misc = (int *)take(sizeof(int) * 8);
-    s.bytes = o;
+    auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return (int)at; };
+    L.lp = take(sizeof(LineP) * P.Lmax);            // hottest first: offset 0
+    L.nmask = take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
+    L.cmask = take(sizeof(unsigned) * (size_t)P.nchunks * P.mwords);
+    L.A64 = take(sizeof(double) * P.Lmax);
+    L.rc64 = take(sizeof(double) * P.Lmax);
+    L.theta = take(sizeof(double) * P.ndim_pad);
+    L.uarr = take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * P.Lmax);
+    L.farp = take(P.scratch_in_flux ? 0 : sizeof(float) * (size_t)P.nchunks * (FF_NC * P.nslots + 1));
+    L.taps = take(sizeof(float) * (2 * P.nmax4 + 8));
+    L.red = take(sizeof(double) * 64);
+    L.misc = take(sizeof(int) * 8);
+    L.flux = take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
+    L.bytes = (int)o;
+    return L;
+}
+
+__device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem &P) {
+    FastSmem s;
+    s.theta = (double *)(base + P.lay.theta);
+    s.A64 = (double *)(base + P.lay.A64);
+    s.rc64 = (double *)(base + P.lay.rc64);
+    s.lp = (LineP *)(base + P.lay.lp);
+    s.uarr = (float *)(base + P.lay.uarr);
+    s.nmask = (unsigned *)(base + P.lay.nmask);
+    s.cmask = (unsigned *)(base + P.lay.cmask);
+    s.farp = (float *)(base + P.lay.farp);
+    s.taps = (float *)(base + P.lay.taps);
+    s.flux = (float *)(base + P.lay.flux);
+    s.red = (double *)(base + P.lay.red);
+    s.misc = (int *)(base + P.lay.misc);
+    s.bytes = (size_t)P.lay.bytes;
     return s;
 }
 
@@ -209,6 +229,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         if (b >= Bt.B) break;
         const double *row = Bt.params + b * Bt.ld;
         const int nrow = row_length(P, flags);
+        MCALF_CHK(nrow <= P.ndim_pad, 0);
+        MCALF_CHK(!P.check_selftest, 31);
         for (int i = tid; i < nrow; i += nthreads) S.theta[i] = load_theta(P, row, i, flags);   // rows may be longer than the CTA
         __syncthreads();
         const SampleHead h = parse_head(P, S.theta, flags);
@@ -219,6 +241,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             double logN, z, bk;
             int li;
             line_source(P, h, S.theta, t, logN, z, bk, li);
+            MCALF_CHK(t < P.Lmax && li >= 0 && li <= P.nlines, 1);
             const Line64 L = line_setup64(logN, z, bk, P.line_wrest[li], P.line_f[li], P.line_gamma[li], P.lam_ref);
             S.A64[t] = L.A;
             S.rc64[t] = L.rc;
@@ -238,6 +261,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // hand the sample to the fp64 kernel
             if (tid == 0) {
                 const unsigned int slot = atomicAdd(Bt.fallback_count, 1u);
+                MCALF_CHK((long long)slot < Bt.B, 10);
                 Bt.fallback_list[slot] = (int)b;
                 if (Bt.fallback_flag) *Bt.fallback_flag = 1;
             }
@@ -273,6 +297,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         const int cls = cact ? chunk_class(L.x, Uh, ds, L.z, L.w, P.eps_cull, P.eps_far) : -1;
                         if (cls == 3) farfield_accumulate(L.x, Uh, ds, L.z, L.y, C);
                         if (cls == 1 || cls == 2) {
+                            // scratch stays inside the chunk's own slice of the depth buffer (or inside uarr)
+                            MCALF_CHK(P.scratch_in_flux ? (uslice + t >= S.flux + P.halo + P.chunks[cs].start && uslice + t < S.flux + P.halo + P.chunks[cs].start + P.chunks[cs].len)
+                                                        : (t < P.Lmax), 3);
+                            MCALF_CHK(cs * MW + (t >> 5) < P.nchunks * P.mwords, 2);
                             uslice[t] = Uh;
                             atomicOr(&S.nmask[cs * MW + (t >> 5)], 1u << (t & 31));
                             if (cls == 2) atomicOr(&S.cmask[cs * MW + (t >> 5)], 1u << (t & 31));
@@ -287,6 +315,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         }
                     }
                     if (cact) {
+                        MCALF_CHK(P.scratch_in_flux ? (fslice >= S.flux + P.halo + P.chunks[cs].start && fslice + (FF_NC - 1) * NS + slot < S.flux + P.halo + P.chunks[cs].start + P.chunks[cs].len)
+                                                    : ((FF_NC - 1) * NS + slot < fstride), 3);
 #pragma unroll
                         for (int m = 0; m < FF_NC / 2; ++m) {
                             fslice[(2 * m) * NS + slot] = C[m].x;
@@ -306,8 +336,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             if (lane == 0) c = atomicAdd(&S.misc[3], 1);
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
+            MCALF_CHK(c >= 0 && c < P.nchunks, 13);
             const ChunkDesc cd = P.chunks[c];
             const int NS = P.nslots;
+            MCALF_CHK(cd.start >= 0 && cd.len >= 1 && cd.len <= CHUNK_PIXELS && cd.start + cd.len <= P.npix, 13);
             const float *fslice = P.scratch_in_flux ? S.flux + P.halo + cd.start + (c & 31) : S.farp + (size_t)c * (FF_NC * NS + 1);
             const float *uslice = P.scratch_in_flux ? fslice + (FF_NC * NS + 1) : S.uarr + (size_t)c * P.Lmax;
             // rows (32 consecutive pixels) are held in pairs: {row 2j, row 2j+1} in one 64-bit register pair,
@@ -316,6 +348,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             constexpr int PX2 = PX / 2;
             F2 d[PX2], tau[PX2];
             const float2 *dh2 = P.dhi2 + cd.start + lane;
+            MCALF_CHK(cd.start + lane + 64 * (PX2 - 1) < P.npix + CHUNK_PIXELS, 5);
 #pragma unroll
             for (int j = 0; j < PX2; ++j) {
                 const float2 v = __ldg(dh2 + 64 * j);
@@ -355,6 +388,8 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
                     const int bit = __ffs(m) - 1;
                     const int t = (w << 5) + bit;
+                    MCALF_CHK(t < h.nact && t < P.Lmax, 1);
+                    MCALF_CHK(P.scratch_in_flux ? (uslice + t < S.flux + P.halo + cd.start + cd.len) : (t < P.Lmax), 3);
                     const float4 *lp4 = reinterpret_cast<const float4 *>(&S.lp[t]);
                     const float4 r0 = lp4[0], r1 = lp4[1], r2 = lp4[2];
                     LineP L;
@@ -394,6 +429,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             __syncwarp();        // the chunk's pass-A scratch (read above) lives where its depth goes now
             {
                 float *dst = S.flux + P.halo + cd.start + lane;
+                MCALF_CHK(P.halo + cd.start + cd.len <= P.halo + P.npix, 6);
                 if (cd.len == CHUNK_PIXELS) {
 #pragma unroll
                     for (int j = 0; j < PX2; ++j) {
@@ -421,9 +457,11 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             for (int j = tid; j < H; j += nthreads) {
                 int src = (npix - 1 - j) % npix;
                 if (src < 0) src += npix;
+                MCALF_CHK(src >= 0 && src < npix && H - 1 - j >= 0, 7);
                 S.flux[H - 1 - j] = S.flux[H + src];
             }
             const int tail = H + 8 + (P.npix4 - npix);
+            MCALF_CHK(H + npix + tail <= 2 * P.halo + P.npix4 + 8, 7);
             for (int j = tid; j < tail; j += nthreads) S.flux[H + npix + j] = S.flux[H + (j % npix)];
         }
         __syncthreads();
@@ -441,6 +479,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             const int o0 = g << 2;
             const float4 *xin = reinterpret_cast<const float4 *>(S.flux + (P.halo + o0 - n4));
             const float4 *gin = reinterpret_cast<const float4 *>(S.taps);
+            MCALF_CHK(P.halo + o0 - n4 >= 0 && P.halo + o0 - n4 + 4 * (nb + 1) <= 2 * P.halo + P.npix4 + 8, 8);
+            MCALF_CHK(4 * nb <= 2 * P.nmax4 + 8, 4);
+            MCALF_CHK(g < P.npix4 / 4, 9);
             float4 xl = xin[0];
             float o_0 = 0.f, o_1 = 0.f, o_2 = 0.f, o_3 = 0.f;
             for (int mb = 0; mb < nb; ++mb) {
@@ -471,6 +512,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 for (int r = 0; r < 4; ++r) {
                     const int o = o0 + r;
                     if (o < P.npix) {
+                        MCALF_CHK(b >= 0 && b < Bt.B, 11);
                         const double md = h.cont - h.cont * (double)out[r];
                         if (Bt.flux_out) {
                             if (flags & MCALF_F_FLUX_F64) ((double *)Bt.flux_out)[b * (long long)P.npix + o] = md;
@@ -682,10 +724,7 @@ __global__ void mcalf_ffma_peak_kernel(float *out, int iters) {
 // ---------------------------------------------------------------------------------------------
 namespace mcalf {
 
-size_t fast_smem_bytes(const DevProblem &P, int nwarps) {
-    (void)nwarps;
-    return carve(nullptr, P).bytes;
-}
+SmemLayout fast_smem_layout(const DevProblem &P) { return make_layout(P); }
 
 size_t fp64_smem_bytes(const DevProblem &P) {
     return sizeof(double) * ((size_t)P.ndim_pad + 4 * (size_t)P.Lmax + P.nmax + 1 + 64 + P.npix);
@@ -748,6 +787,21 @@ cudaError_t launch_voigt_h(int mode, const double *u, const double *a, long long
     if (grid < 1) grid = 1;
     mcalf_voigt_h_kernel<<<grid, 256, 0, st>>>(mode, u, a, n, out);
     return cudaGetLastError();
+}
+
+// checked build: read and clear the device-side violation mask (0 in the product build)
+cudaError_t check_flag_fetch(unsigned int *mask) {
+    *mask = 0u;
+#if defined(MCALF_CHECK)
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyFromSymbol(mask, mcalf_check_flag, sizeof(unsigned int));
+    if (e != cudaSuccess) return e;
+    const unsigned int zero = 0u;
+    return cudaMemcpyToSymbol(mcalf_check_flag, &zero, sizeof(unsigned int));
+#else
+    return cudaSuccess;
+#endif
 }
 
 cudaError_t launch_ffma_peak(float *out, int grid, int threads, int iters, cudaStream_t st) {

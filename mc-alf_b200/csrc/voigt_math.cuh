@@ -31,6 +31,21 @@
 
 #include "voigt_tables.inc"
 
+// Bounds-checked build (-DMCALF_CHECK, libmcalf_b200_check.so): every shared-memory / global index the fp32
+// kernel forms is validated; a violation sets a bit of a device-side flag that the C-ABI turns into
+// MCALF_E_CUDA ("bounds check failed").  compute-sanitizer is closed on the GPU pool, so this is the memory-
+// safety tool of the test suite (tests/test_gpu_checked.py).  In the product build the macro is empty.
+#if defined(MCALF_CHECK) && defined(__CUDACC__)
+namespace mcalf { static __device__ unsigned int mcalf_check_flag = 0u; }
+#endif
+#if defined(MCALF_CHECK) && defined(__CUDA_ARCH__)
+#define MCALF_CHK(cond, bit) do { if (!(cond)) atomicOr(&::mcalf::mcalf_check_flag, 1u << (bit)); } while (0)
+#else
+#define MCALF_CHK(cond, bit) ((void)0)
+#endif
+// bits: 0 theta  1 line table  2 masks  3 pass-A scratch  4 taps  5 pixel pair tables  6 depth store  7 halo
+//       8 stencil window  9 per-pixel tables  10 fallback list  11 flux output  12 H1 table  13 chunk table
+
 namespace mcalf {
 
 constexpr double C_KMS = 2.9979245e5;        // hires_fitter.py:65
@@ -186,6 +201,10 @@ MCALF_HD F2 depth32_2(F2 x) {
 
 // tab: the table's copy in shared memory (kernels), or null for the global/host copy
 MCALF_HD G1Row g1_row(int j, const G1Row *tab = nullptr) {
+    MCALF_CHK(j >= 0 && j < MCALF_G1_N, 12);
+#if defined(MCALF_CHECK)
+    j = j < 0 ? 0 : (j >= MCALF_G1_N ? MCALF_G1_N - 1 : j);
+#endif
 #if defined(__CUDA_ARCH__)
     const float4 v = tab ? reinterpret_cast<const float4 *>(tab)[j] : __ldg(reinterpret_cast<const float4 *>(g1_tab_dev) + j);
     G1Row r; r.c0 = v.x; r.c1 = v.y; r.c2 = v.z; r.c3 = v.w;
@@ -370,20 +389,43 @@ struct alignas(16) LineP {
     float A_lo, pad0, pad1, pad2;
 };
 
+// 10^x for x in [-300, 300] to ~2e-8 relative: 2^(i + f) with i = rint(x log2 10) and a degree-7 polynomial
+// for 2^f on |f| <= 1/2.  kappa multiplies an fp32 H, so fp32-level accuracy is all it needs; the fp64 library
+// exp10 was the longest dependent chain of the per-sample set-up (one thread per line, everybody else waiting).
+MCALF_HD double pow10_fast(double x) {
+    const double t = x * 3.32192809488736234787;
+    const double fi = rint(t);
+    const double f = t - fi;                               // exact difference of close doubles
+    // 2^f = exp(f ln2), Taylor/minimax to degree 7 in fp64 (cheap: 7 FMAs), |error| < 2e-9
+    const double g = f * 0.69314718055994530942;
+    double p = 1.0 / 5040.0;
+    p = fma(p, g, 1.0 / 720.0);
+    p = fma(p, g, 1.0 / 120.0);
+    p = fma(p, g, 1.0 / 24.0);
+    p = fma(p, g, 1.0 / 6.0);
+    p = fma(p, g, 0.5);
+    p = fma(p, g, 1.0);
+    p = fma(p, g, 1.0);
+    int e = (int)fi;
+    e = e < -1000 ? -1000 : (e > 1000 ? 1000 : e);
+#if defined(__CUDA_ARCH__)
+    return scalbn(p, e);
+#else
+    return ldexp(p, e);
+#endif
+}
+
 MCALF_HD Line64 line_setup64(double logN, double z, double b_kms, double wrest, double f, double gamma,
                              double lam_ref) {
     Line64 L;
     const double lamc = wrest * (1.0 + z);
-    const double wrest_cm = wrest * 1e-8, b_cms = b_kms * 1e5;
-    L.A = (C_KMS / b_kms) * (lamc / lam_ref);
+    const double inv_b = 1.0 / b_kms;                      // the only divisions: 1/b and lam_ref/lamc
     L.rc = lam_ref / lamc;
-#if defined(__CUDA_ARCH__)
-    const double cold = exp10(logN);
-#else
-    const double cold = pow(10.0, logN);
-#endif
-    L.kappa = TAU_CONST * cold * f * wrest_cm / b_cms;
-    L.a = gamma * wrest_cm / (4.0 * PI_D * b_cms);
+    L.A = (C_KMS * inv_b) * (lamc / lam_ref);
+    const double cold = pow10_fast(logN);
+    const double wb = (wrest * 1e-8) * (inv_b * 1e-5);     // wrest_cm / b_cms
+    L.kappa = TAU_CONST * cold * f * wb;
+    L.a = gamma * wb * (1.0 / (4.0 * PI_D));
     return L;
 }
 
@@ -405,7 +447,11 @@ constexpr float U_CORE_MARGIN = 6.01f;             // sqrt(S_CUT) + U_CUT_MARGIN
 
 MCALF_HD bool line_cut(double kappa, double a, float &scut) {
     const double c1 = kappa * a / SQRTPI_D;
-    double s = (kappa > 0.0) ? log(kappa) + LN_INV_EPS_GAUSS : (double)MCALF_S_WIDE;
+#if defined(__CUDA_ARCH__)
+    double s = (kappa > 0.0) ? (double)__logf((float)kappa) + LN_INV_EPS_GAUSS : (double)MCALF_S_WIDE;   // (the boundary needs no precision)
+#else
+    double s = (kappa > 0.0) ? (double)logf((float)kappa) + LN_INV_EPS_GAUSS : (double)MCALF_S_WIDE;
+#endif
     if (!(s > (double)MCALF_S_WIDE)) s = (double)MCALF_S_WIDE;
     const bool wide = s < (double)S_CUT - 0.5 && c1 * MCALF_WING_PW_ERR <= EPS_WING * s;
     scut = wide ? (float)s : S_CUT;

@@ -1,7 +1,3 @@
-nvidia-smi -L
-python -m pytest tests/test_gpu_multirank.py -q -s -m gpu -p no:cacheprovider > gpurun_out/mr_r02d.log 2>&1; tail -15 gpurun_out/mr_r02d.log
-for mode in auto nccl; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --gather $mode > gpurun_out/bench2_$mode.json 2> gpurun_out/bench2_$mode.err
-echo "exit $?"; tail -3 gpurun_out/bench2_$mode.err; python -c "
-import json; d=json.load(open('gpurun_out/bench2_$mode.json')); print(d['value'], d['e2e']['value']); [print(s) for s in d['strong']]"
-done
+python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider -x -k "not fuzz and not checked" > gpurun_out/tests_r02f.log 2>&1; tail -3 gpurun_out/tests_r02f.log
+python bench.py --no-cpu --no-strong > gpurun_out/bench_r02f.json 2> gpurun_out/bench_r02f.err; python -c "
+import json; d=json.load(open('gpurun_out/bench_r02f.json')); print(d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline']['kernel_ms']); [print(x) for x in d['sweep']['cfg4']]; [print(x['cfg'], x['device'], x['e2e_pinned']) for x in d['sweep']['configs']]"
