@@ -205,8 +205,10 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
     return s;
 }
 
-template <bool STATS, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB)
+// STATS: path counters (bench / diagnostics).  EXTRAS: the per-pixel outputs (model flux, Asymmlike counts); the
+// plain logL instantiation does not carry that code, which keeps the hot kernel smaller in the instruction cache.
+template <bool STATS, bool EXTRAS>
+__global__ void __launch_bounds__(1024, 1)
 mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ BatchArgs Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -474,7 +476,6 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         const int ngroups = P.npix4 >> 2;
         // taps G[m] are non-zero for m in [n4 - n, n4 + n]: blocks of four taps up to the one holding n4 + n
         const int nb = ((n4 + S.misc[6]) >> 2) + 1;
-        const bool extras = Bt.flux_out != nullptr || P.asymmlike;
         for (int g = tid; g < ngroups; g += nthreads) {
             const int o0 = g << 2;
             const float4 *xin = reinterpret_cast<const float4 *>(S.flux + (P.halo + o0 - n4));
@@ -506,7 +507,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             F2 p2 = mul2(mul2(f2(ww.x, ww.y), ra), ra);
             p2 = fma2(mul2(f2(ww.z, ww.w), rb), rb, p2);
             const float part = p2.x + p2.y;
-            if (extras) {
+            if (EXTRAS) {
                 const float out[4] = {o_0, o_1, o_2, o_3};
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
@@ -529,23 +530,23 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             acc += (double)part;
         }
         acc = warp_sum(acc);
-        if (P.asymmlike) { cnt5 = warp_sum_int(cnt5); cnt4 = warp_sum_int(cnt4); }
+        if (EXTRAS && P.asymmlike) { cnt5 = warp_sum_int(cnt5); cnt4 = warp_sum_int(cnt4); }
         if (lane == 0) {
             S.red[warp] = acc;
-            if (P.asymmlike) { ((int *)(S.red + 32))[warp] = cnt5; ((int *)(S.red + 32))[32 + warp] = cnt4; }
+            if (EXTRAS && P.asymmlike) { ((int *)(S.red + 32))[warp] = cnt5; ((int *)(S.red + 32))[32 + warp] = cnt4; }
         }
         __syncthreads();
         if (warp == 0) {
             double v = lane < nwarps ? S.red[lane] : 0.0;
             v = warp_sum(v);
             int c5 = 0, c4 = 0;
-            if (P.asymmlike) {
+            if (EXTRAS && P.asymmlike) {
                 c5 = warp_sum_int(lane < nwarps ? ((int *)(S.red + 32))[lane] : 0);
                 c4 = warp_sum_int(lane < nwarps ? ((int *)(S.red + 32))[32 + lane] : 0);
             }
             if (lane == 0) {
                 double logl = P.logC - 0.5 * v;
-                if (P.asymmlike && ((double)c5 > P.asym_t5 || (double)c4 > P.asym_t4)) logl = -INFINITY;   // :296-303
+                if (EXTRAS && P.asymmlike && ((double)c5 > P.asym_t5 || (double)c4 > P.asym_t4)) logl = -INFINITY;   // :296-303
                 store_results(Bt, b, logl, v + P.chi2_add);
             }
         }
@@ -743,25 +744,23 @@ static cudaError_t raise_smem_limit(K kernel, size_t optin, size_t *static_bytes
 }
 
 cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes) {
-    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, 1024, 1>, optin_bytes, fast_static_bytes);
+    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, false>, optin_bytes, fast_static_bytes);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<true, 1024, 1>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, true>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<false, 256, 5>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<true, true>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
     return raise_smem_limit(mcalf_fp64_kernel, optin_bytes, nullptr);
 }
 
-// dense = the 48-register build (CTAs of at most 256 threads, five or more per SM)
-cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm) {
-    if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, 256, 5>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, 1024, 1>, threads, smem);
+cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false>, threads, smem);
 }
 
-cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st) {
-    if (Bt.stats) mcalf_fast_kernel<true, 1024, 1><<<grid, threads, smem, st>>>(P, Bt);
-    else if (dense && threads <= 256) mcalf_fast_kernel<false, 256, 5><<<grid, threads, smem, st>>>(P, Bt);
-    else mcalf_fast_kernel<false, 1024, 1><<<grid, threads, smem, st>>>(P, Bt);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st) {
+    if (Bt.stats) mcalf_fast_kernel<true, true><<<grid, threads, smem, st>>>(P, Bt);
+    else if (Bt.flux_out != nullptr || P.asymmlike) mcalf_fast_kernel<false, true><<<grid, threads, smem, st>>>(P, Bt);
+    else mcalf_fast_kernel<false, false><<<grid, threads, smem, st>>>(P, Bt);
     return cudaGetLastError();
 }
 

@@ -510,6 +510,26 @@ MCALF_HD int chunk_class(float A_hi, float U_hi, float ds, float c1, float ucm, 
     return 1;
 }
 
+// the binomial pairs {b[2m], b[2m+1]} of the three series: constant-bank operands on the device (the compiler would
+// otherwise rebuild the twelve 64-bit constants with two UMOVs each on every trip of the classification loop)
+#if defined(__CUDACC__)
+static __constant__ float2 ff_b1_dev[5] = {{1.f, 2.f}, {3.f, 4.f}, {5.f, 6.f}, {7.f, 8.f}, {9.f, 10.f}};
+static __constant__ float2 ff_b2_dev[5] = {{1.f, 4.f}, {10.f, 20.f}, {35.f, 56.f}, {84.f, 120.f}, {165.f, 220.f}};
+static __constant__ float2 ff_b3_dev[5] = {{1.f, 6.f}, {21.f, 56.f}, {126.f, 252.f}, {462.f, 792.f}, {1287.f, 2002.f}};
+#endif
+#if defined(__CUDA_ARCH__)
+#define FF_B1(m) f2(ff_b1_dev[m].x, ff_b1_dev[m].y)
+#define FF_B2(m) f2(ff_b2_dev[m].x, ff_b2_dev[m].y)
+#define FF_B3(m) f2(ff_b3_dev[m].x, ff_b3_dev[m].y)
+#else
+static const float ff_b1_host[10] = {1.f, 2.f, 3.f, 4.f, 5.f, 6.f, 7.f, 8.f, 9.f, 10.f};
+static const float ff_b2_host[10] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f, 84.f, 120.f, 165.f, 220.f};
+static const float ff_b3_host[10] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f, 462.f, 792.f, 1287.f, 2002.f};
+#define FF_B1(m) f2(ff_b1_host[2 * (m)], ff_b1_host[2 * (m) + 1])
+#define FF_B2(m) f2(ff_b2_host[2 * (m)], ff_b2_host[2 * (m) + 1])
+#define FF_B3(m) f2(ff_b3_host[2 * (m)], ff_b3_host[2 * (m) + 1])
+#endif
+
 // Add one far line's expansion coefficients (in x = delta/ds) to C[0..FF_DEG], held as pairs
 // {C[2m], C[2m+1]} (packed arithmetic: two coefficients per instruction).
 MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, float a2, F2 *C2) {
@@ -521,14 +541,11 @@ MCALF_HD void farfield_accumulate(float A_hi, float U_hi, float ds, float c1, fl
     const float T2 = T1 * v * (1.5f - a2);
     const float T3 = T1 * v * v * 3.75f;
     // binom(-2,n) = (-1)^n (n+1), binom(-4,n) = (-1)^n C(n+3,3), binom(-6,n) = (-1)^n C(n+5,5)
-    const float b2[10] = {1.f, 4.f, 10.f, 20.f, 35.f, 56.f, 84.f, 120.f, 165.f, 220.f};
-    const float b3[10] = {1.f, 6.f, 21.f, 56.f, 126.f, 252.f, 462.f, 792.f, 1287.f, 2002.f};
     const F2 T12 = f2(T1), T22 = f2(T2), T32 = f2(T3), ss = f2(s * s);
     F2 sn = f2(1.0f, s);
 #pragma unroll
     for (int m = 0; 2 * m <= FF_DEG; ++m) {
-        const int n = 2 * m;
-        const F2 t = fma2(f2((float)(n + 1), (float)(n + 2)), T12, fma2(f2(b2[n], b2[n + 1]), T22, mul2(f2(b3[n], b3[n + 1]), T32)));
+        const F2 t = fma2(FF_B1(m), T12, fma2(FF_B2(m), T22, mul2(FF_B3(m), T32)));
         C2[m] = fma2(sn, t, C2[m]);
         sn = mul2(sn, ss);
     }
