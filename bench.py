@@ -44,11 +44,13 @@ WORKLOAD = "cfg4: 8192 px x 20 comps x 2 lines (CIV doublet), free specres+conti
 # MUFU = 1); derivation in DESIGN.md section 5
 FLOP_PAIR_CLASS = 18     # chunk_class per (line, chunk) pair
 FLOP_PAIR_FAR = 74       # farfield_accumulate per far pair (8 coefficients x 3 series)
-FLOP_NEAR_EVAL = 14      # direct wing form per (line, pixel): u, s (4), Horner with pre-scaled coefficients (8), accumulate (2); rcp not counted
-FLOP_MIXED_VOTE = 4      # u and s of every pixel of a mixed (line, chunk) pair before the row pair's vote
-FLOP_CORE_LEAN = 45      # per pixel evaluated with the short core form (coordinate fix-up 6, H1 cubic 6, Gaussian factors 10, table index 7, combine 8, kappa 1, accumulate 1, u/s shared)
-FLOP_CORE_PRECISE = 85   # per pixel with the two-float form (two-float coordinate and u^2, polynomial exp)
-FLOP_CHUNK = 64          # summing the slots' far-field partials, per (sample, chunk)
+FLOP_NEAR_EVAL = 14      # direct wing form per (line, pixel) of a wing-only pair: u, s (4), Horner with pre-scaled coefficients (8), fused accumulate (2); rcp is MUFU, not counted
+FLOP_MIXED_VOTE = 4      # u and s of every pixel of a mixed (line, chunk) pair, computed before the row pair's vote
+FLOP_MIXED_WING = 10     # ... plus Horner and accumulate where the row pair takes the wing form
+FLOP_CORE_LEAN = 33      # ... or the short core form: coordinate fix-up 5, u^2 and exponent 2, table index 5, H1 cubic 6, a^2 factors 8, combine 5, kappa and accumulate 2 (EX2, min/max not counted)
+FLOP_CORE_PRECISE = 80   # ... or the two-float form (two-float coordinate and u^2, polynomial exp)
+FLOP_STRADDLE = 11       # extra per pixel of a row pair that needs both forms (wing value + select)
+FLOP_CHUNK = 256         # summing the slots' far-field partials: 8 adds on all 32 lanes, per (sample, chunk)
 FLOP_PIXEL = 48          # far-field polynomial (15) + depth32 (23) + residual / chi-square (10); stencil: 2 per padded tap
 CHUNK = 256
 # SURVEY 8d canonical counts (Weideman-32 core, 3-term asymptotic wing)
@@ -489,13 +491,16 @@ def run_ours(args):
 
 
 def model_flops(st, geo, B, npix, n):
-    """Executed FP32 flops of one launch from the kernel's own path counters (FMA = 2, add/mul = 1; FFMA2 = 4)."""
+    """Executed FP32 flops of one launch from the kernel's own path counters (FMA = 2, add/mul = 1; FFMA2 = 4; what the
+    FMA pipe executes: MUFU, min/max, compares and the fp64 set-up are not counted).  Cross-checked against the ncu
+    opcode histogram (tools/ncu_opcodes.py): the two agree within a few per cent."""
     taps_padded = 2 * (4 * np.ceil(n / 4)) + 4
     pairs = st["evals_total"] / CHUNK
-    near_evals = st["evals_wing"] + st["evals_mixed"] - st["evals_core"] + st["evals_core_straddle"]
     lean = st["evals_core"] - st["evals_core_precise"]
-    return (FLOP_PAIR_CLASS * pairs + FLOP_PAIR_FAR * st["evals_far"] / CHUNK + FLOP_NEAR_EVAL * near_evals
-            + FLOP_MIXED_VOTE * st["evals_mixed"] + FLOP_CORE_LEAN * lean + FLOP_CORE_PRECISE * st["evals_core_precise"]
+    mixed_wing = st["evals_mixed"] - st["evals_core"]
+    return (FLOP_PAIR_CLASS * pairs + FLOP_PAIR_FAR * st["evals_far"] / CHUNK + FLOP_NEAR_EVAL * st["evals_wing"]
+            + FLOP_MIXED_VOTE * st["evals_mixed"] + FLOP_MIXED_WING * mixed_wing + FLOP_CORE_LEAN * lean
+            + FLOP_CORE_PRECISE * st["evals_core_precise"] + FLOP_STRADDLE * st["evals_core_straddle"]
             + FLOP_CHUNK * geo["nchunks"] * B + npix * (FLOP_PIXEL * B + 2.0 * taps_padded.sum()))
 
 

@@ -84,6 +84,7 @@ def load():
     if _lib is not None:
         return _lib
     path = CHECK_LIB_PATH if os.environ.get("MCALF_B200_CHECK") == "1" else LIB_PATH
+    path = os.environ.get("MCALF_B200_LIB", path)        # development: an experimental build of the same ABI
     if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -m mcalf_b200.build` (nvcc, sm_100a). "
                           "There is no CPU fallback." % path)
