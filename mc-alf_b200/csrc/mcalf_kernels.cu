@@ -414,6 +414,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const float2 *dl2 = P.dlo2 + cd.start + lane;
 #pragma unroll
                     for (int j = 0; j < PX2; ++j) {
+                        const float2 dlv = __ldg(dl2 + 64 * j);      // issued before the votes: its latency hides behind them
                         const F2 u = fma2(A2, d[j], U2);
                         const F2 s2 = fma2(u, u, a22);
                         const bool all_wing = __all_sync(0xffffffffu, s2.x >= L.scut && s2.y >= L.scut);
@@ -422,7 +423,6 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                             continue;
                         }
                         const bool all_tab = __all_sync(0xffffffffu, fabsf(u.x) <= U_TAB && fabsf(u.y) <= U_TAB);
-                        const float2 dlv = __ldg(dl2 + 64 * j);
                         tau[j] = mixed_pair_tau(pair_kind(false, all_tab), tau[j], L, u, s2, d[j], f2(dlv.x, dlv.y), Uh64, Ul, g1_smem);
                         if (STATS) { st_core += 2; st_corep += L.kappa > KAPPA_LEAN ? 2 : 0; st_both += all_tab ? 0 : 2; }
                     }

@@ -114,3 +114,55 @@ def test_batched_nested_sampler_on_a_gaussian():
     s, _ = equal_weight_resample(r, 2000)
     assert np.allclose(s[:, 1:].mean(axis=0), [0.4, 0.6], atol=0.01)
     assert r["nlaunch"] * 1024 + 300 >= r["ncall"]
+
+
+def test_dynesty_driver_batches_every_block(tmp_path):
+    """``drivers.run_dynesty`` against a stand-in dynesty: every block of proposals reaches the fitter as ONE batched
+    call (prior transform and likelihood), the chain files come out in the reference's formats, and the reference's
+    own reader understands them."""
+    from tests import fake_solvers
+    from mcalf_b200 import chains, drivers
+    fake_solvers.install_dynesty()
+    try:
+        f = FakeFitter()
+        f.bounds = [(0.0, 2.0)] * 3
+        base = str(tmp_path / "chain_0")
+        out = drivers.run_dynesty(f, base, queue_size=64, seed=5)
+        nb = fake_solvers.DynamicNestedSampler.nblocks
+        assert f.batches[:2 * nb] == [64] * (2 * nb)             # nblocks x (prior transform, likelihood), 64 points each
+        assert out["launches"] == 2 * nb and out["scalar_fallbacks"] == 0
+        assert f.batches[-1] == len(out["samples"])              # the equal-weight samples re-evaluated in one launch
+        lnz, err, lh, post = chains.read_chains(base, return_sorted=False)
+        assert lnz == out["logz"] and np.allclose(lh, out["logl"]) and post.shape == out["samples"].shape
+        first = open(base + "_equal_weights.txt").readline().split()
+        assert len(first) == 2 + 3 and float(first[0]) == 1.0 and float(first[1]) == -2.0 * out["logl"][0]
+    finally:
+        fake_solvers.uninstall("dynesty")
+
+
+def test_jax_likelihood_adapter_batches_under_vmap():
+    """``solvers.jax_likelihood`` (what ``get_jax_likelihood()`` returns, cli.py:237) against a stand-in jax: a vmapped
+    block of live points reaches ``lnlhood_batch`` once, float32 in and out as jaxns runs it."""
+    from tests import fake_solvers
+    from mcalf_b200.solvers import jax_likelihood
+    jax = fake_solvers.install_jax()
+    try:
+        f = FakeFitter()
+        ll = jax_likelihood(f)
+        one = ll(np.array([1.0, 2.0, 3.0], dtype=np.float32))
+        assert one.shape == () and one.dtype == np.float32 and float(one) == -14.0 and f.batches == [1]
+        block = np.arange(30, dtype=np.float32).reshape(10, 3)
+        out = jax.vmap(ll)(block)
+        assert out.shape == (10,) and out.dtype == np.float32 and f.batches == [1, 10]
+        assert np.allclose(out, -np.sum(block.astype(np.float64) ** 2, axis=1))
+    finally:
+        fake_solvers.uninstall("jax")
+
+
+def test_drivers_need_their_sampler():
+    import pytest
+    from mcalf_b200 import drivers
+    with pytest.raises(ImportError, match="dynesty is required"):
+        drivers.run_dynesty(FakeFitter(), "/tmp/none")
+    with pytest.raises(ImportError, match="jaxns is required"):
+        drivers.run_jaxns(FakeFitter(), "/tmp/none")
