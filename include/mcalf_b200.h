@@ -151,6 +151,8 @@ int mcalf_reset_stats(mcalf_ctx *ctx);
  *          "collect_stats" 0/1; "check_selftest" 0/1 (checked build only: the next launches report a violation on purpose);
  *          "threads" CTA size of the fp32 kernel (multiple of 32, 0 = automatic);
  *          "ctas_per_sm" persistent CTAs per SM (0 = what the occupancy calculator allows);
+ *          "dense" 1/0/-1: force / forbid / choose automatically (default) the 48-register build of the fp32 kernel
+ *                  (CTAs of <= 256 threads; chosen when it seats more CTAs per SM on a long spectrum);
  *          "slice" samples per pipelined slice of the host-pointer path. */
 int mcalf_set_option(mcalf_ctx *ctx, const char *name, double value);
 int mcalf_get_option(mcalf_ctx *ctx, const char *name, double *value);

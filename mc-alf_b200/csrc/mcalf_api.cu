@@ -96,7 +96,7 @@ struct mcalf_ctx {
     Slot zc_slot;
     size_t pipe_dout_cap = 0, pipe_hout_cap = 0;
     unsigned long long *d_stats = nullptr;
-    int threads = 0, threads_small = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0;
+    int threads = 0, threads_small = 0, ctas_per_sm = 0, threads_opt = 0, ctas_opt = 0, dense = 0, dense_opt = -1;
     size_t smem_fast = 0, smem_fp64 = 0;
     long long slice = 65536;
     int collect_stats = 0;
@@ -182,15 +182,20 @@ int choose_launch(mcalf_ctx *c) {
                     (size_t)prop.sharedMemPerBlockOptin);
     c->threads = nwarps * 32;
     c->smem_fast = smem;
-    int occ = 0;
-    CU(fast_occupancy(c->threads, c->smem_fast, &occ));   // accounts for the kernel's static shared memory too
+    int occ = 0, occ_dense = 0;
+    CU(fast_occupancy(c->threads, c->smem_fast, 0, &occ));   // accounts for the kernel's static shared memory too
+    if (c->threads <= 256 && c->dense_opt != 0) CU(fast_occupancy(c->threads, c->smem_fast, 1, &occ_dense));
+    // the 48-register build is ~4 % slower per warp: it pays only where it seats more CTAs AND the samples are long
+    // (measured: cfg 4, 8192 px, 5 instead of 4 CTAs: +3 %; cfg 2, 1998 px, 10 instead of 8 CTAs: -3 %)
+    c->dense = (occ_dense > occ && (c->dense_opt == 1 || P.nchunks >= 16)) ? 1 : 0;
+    if (c->dense) occ = occ_dense;
     if (occ < 1) return fail(MCALF_E_RESOURCE, "fp32 kernel does not fit an SM (threads %d, smem %zu)", c->threads, smem);
     c->ctas_per_sm = c->ctas_opt > 0 ? std::min(c->ctas_opt, occ) : occ;
     c->threads_small = 0;
     {
         const int ts = 32 * std::min(std::max(P.nchunks, 1), 32);
         int occ_s = 0;
-        if (ts > c->threads && fast_occupancy(ts, c->smem_fast, &occ_s) == cudaSuccess && occ_s >= 1) c->threads_small = ts;
+        if (ts > c->threads && fast_occupancy(ts, c->smem_fast, 0, &occ_s) == cudaSuccess && occ_s >= 1) c->threads_small = ts;
     }
     return MCALF_OK;
 }
@@ -290,7 +295,7 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
         // fewer samples than SMs: one CTA per sample, as many warps as the sample has chunks (results do
         // not depend on the CTA size)
         if (n <= c->sm_count && c->threads_opt == 0 && c->threads_small > threads) threads = c->threads_small;
-        CU(launch_fast(c->P, a, grid, threads, c->smem_fast, st));
+        CU(launch_fast(c->P, a, grid, threads, c->smem_fast, threads == c->threads ? c->dense : 0, st));
         // samples outside the fp32 domain were listed by the fast kernel; the fp64 kernel finishes them
         // (exits at once when the list is empty)
         c->kernel_launches += 1;
@@ -881,6 +886,9 @@ int mcalf_set_option(mcalf_ctx *c, const char *name, double value) {
         if (value < 0) return fail(MCALF_E_INVALID, "ctas_per_sm must be >= 0");
         c->ctas_opt = (int)value;
         return choose_launch(c);
+    } else if (!strcmp(name, "dense")) {
+        c->dense_opt = value < 0 ? -1 : (value != 0.0);
+        return choose_launch(c);
     } else if (!strcmp(name, "slice")) {
         if (value < 1) return fail(MCALF_E_INVALID, "slice must be >= 1");
         c->slice = (long long)value;
@@ -898,6 +906,7 @@ int mcalf_get_option(mcalf_ctx *c, const char *name, double *value) {
     else if (!strcmp(name, "collect_stats")) *value = c->collect_stats;
     else if (!strcmp(name, "threads")) *value = c->threads;
     else if (!strcmp(name, "ctas_per_sm")) *value = c->ctas_per_sm;
+    else if (!strcmp(name, "dense")) *value = c->dense;
     else if (!strcmp(name, "slice")) *value = (double)c->slice;
     else return fail(MCALF_E_INVALID, "unknown option '%s'", name);
     return MCALF_OK;

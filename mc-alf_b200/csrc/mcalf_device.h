@@ -63,8 +63,8 @@ struct BatchArgs {
 SmemLayout fast_smem_layout(const DevProblem &P);
 size_t fp64_smem_bytes(const DevProblem &P);
 cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes);
-cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm);
-cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st);
+cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st);
 cudaError_t launch_fp64(const DevProblem &P, const BatchArgs &Bt, const int *idx_list, const unsigned int *idx_count, int grid,
                         size_t smem, cudaStream_t st);
 cudaError_t launch_prior(const DevProblem &P, const double *cube, long long B, long long ld, uint32_t flags, double *out,

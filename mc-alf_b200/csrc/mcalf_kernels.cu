@@ -207,8 +207,11 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
 
 // STATS: path counters (bench / diagnostics).  EXTRAS: the per-pixel outputs (model flux, Asymmlike counts); the
 // plain logL instantiation does not carry that code, which keeps the hot kernel smaller in the instruction cache.
-template <bool STATS, bool EXTRAS>
-__global__ void __launch_bounds__(1024, 1)
+// DENSE: the 48-register build (CTAs of at most 256 threads, five per SM).  ptxas fits the kernel into 48 registers
+// with 20 bytes of spills and some rematerialisation: 4 % slower per warp, so it only pays where it seats a fifth CTA
+// (cfg 4: 40 instead of 32 warps per SM, +3 %; the host picks it, mcalf_api.cu:choose_launch).
+template <bool STATS, bool EXTRAS, bool DENSE>
+__global__ void __launch_bounds__(DENSE ? 256 : 1024, DENSE ? 5 : 1)
 mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ BatchArgs Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -744,23 +747,27 @@ static cudaError_t raise_smem_limit(K kernel, size_t optin, size_t *static_bytes
 }
 
 cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes) {
-    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, false>, optin_bytes, fast_static_bytes);
+    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, false, false>, optin_bytes, fast_static_bytes);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<false, true>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, false, true>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<true, true>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, true, false>, optin_bytes, nullptr);
+    if (e != cudaSuccess) return e;
+    e = raise_smem_limit(mcalf_fast_kernel<true, true, false>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
     return raise_smem_limit(mcalf_fp64_kernel, optin_bytes, nullptr);
 }
 
-cudaError_t fast_occupancy(int threads, size_t smem, int *ctas_per_sm) {
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false>, threads, smem);
+cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm) {
+    if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, true>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, false>, threads, smem);
 }
 
-cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, cudaStream_t st) {
-    if (Bt.stats) mcalf_fast_kernel<true, true><<<grid, threads, smem, st>>>(P, Bt);
-    else if (Bt.flux_out != nullptr || P.asymmlike) mcalf_fast_kernel<false, true><<<grid, threads, smem, st>>>(P, Bt);
-    else mcalf_fast_kernel<false, false><<<grid, threads, smem, st>>>(P, Bt);
+cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st) {
+    if (Bt.stats) mcalf_fast_kernel<true, true, false><<<grid, threads, smem, st>>>(P, Bt);
+    else if (Bt.flux_out != nullptr || P.asymmlike) mcalf_fast_kernel<false, true, false><<<grid, threads, smem, st>>>(P, Bt);
+    else if (dense && threads <= 256) mcalf_fast_kernel<false, false, true><<<grid, threads, smem, st>>>(P, Bt);
+    else mcalf_fast_kernel<false, false, false><<<grid, threads, smem, st>>>(P, Bt);
     return cudaGetLastError();
 }
 

@@ -269,3 +269,19 @@ def test_dynesty_driver_and_jax_adapter_drive_the_real_fitter(tmp_path):
         assert np.array_equal(got, g.lnlhood_batch(P.astype(np.float64)).astype(np.float32))
     finally:
         fake_solvers.uninstall("jax")
+
+
+def test_register_lean_build_gives_the_same_bits():
+    """The 48-register instantiation (five CTAs per SM, chosen automatically on long spectra) is the same arithmetic:
+    forcing it on or off must not change a bit."""
+    o, g = fitters("cfg4")
+    U = np.random.default_rng(12).random((3000, o.ndim))
+    auto = g.lnlhood_batch(U, unit_cube=True)
+    assert g.get_option("dense") == 1.0 and g.geometry()["ctas_per_sm"] == 5      # the automatic choice at cfg 4 on a B200
+    g.set_option("dense", 0)
+    assert g.get_option("dense") == 0.0 and g.geometry()["ctas_per_sm"] == 4
+    assert np.array_equal(g.lnlhood_batch(U, unit_cube=True), auto)
+    g.set_option("dense", 1)
+    assert np.array_equal(g.lnlhood_batch(U, unit_cube=True), auto)
+    o2, g2 = fitters("cfg2")
+    assert g2.get_option("dense") == 0.0                                            # short spectrum: not chosen
