@@ -145,7 +145,7 @@ int mcalf_reset_stats(mcalf_ctx *ctx);
 /* Options: "cull_eps"  (line, chunk) pairs whose optical depth is provably below it are skipped
  *                      (default 0 = never: the reference never skips);
  *          "far_eps"   optical-depth error allowed to a (line, chunk) pair that is folded into the
- *                      chunk's far-field expansion of the Lorentzian wings (default 1e-9; 0 = never);
+ *                      chunk's far-field expansion of the Lorentzian wings (default 3e-9; 0 = never);
  *          "a_max"     damping parameters above it route the sample to the fp64 kernel (default 0.01,
  *                      upper limit 0.02: the validity range of the fp32 line-core series);
  *          "collect_stats" 0/1; "check_selftest" 0/1 (checked build only: the next launches report a violation on purpose);

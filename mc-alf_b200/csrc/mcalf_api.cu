@@ -571,7 +571,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     P.asym_t4 = p->asym_thresh4;
     P.a_max = A_MAX_DEFAULT;
     P.eps_cull = 0.0f;
-    P.eps_far = 1e-9f;
+    P.eps_far = 3e-9f;      // per (line, chunk) pair; measured: 1e-9 -> 3e-9 is +1 % with no change of the achieved accuracy
     P.Lmax = std::max(p->ncompmax * p->nlines + p->nfill, std::max(p->nlines, 1));
     P.lam_ref = p->wave[npix / 2];
     if (!(P.lam_ref > 0.0)) return fail(MCALF_E_INVALID, "non-positive wavelength");
