@@ -76,3 +76,33 @@ def test_sharded_likelihood_nccl_and_peer_stores_bit_identical():
             used.add((key[1], gather))
     print("world", world, "gathers exercised:", sorted(used))
     assert ("nccl", "nccl") in used
+
+
+def test_fitter_on_a_device_that_is_not_torchs_current_one():
+    """a fitter bound to cuda:1 used while torch's current device is cuda:0 -- the stream handed to the library
+    must be cuda:1's, and no call may change the calling thread's current device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs at least two GPUs")
+    import mcalf_b200
+    from mcalf_b200.workloads import config_kwargs
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec, kw = config_kwargs(2, golden)
+    args = (spec, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]))
+    kws = {k: (list(v) if isinstance(v, tuple) else v) for k, v in kw.items() if k not in ("fitrange", "fitlines", "ncomp")}
+    torch.cuda.set_device(0)
+    g0 = mcalf_b200.als_fitter(*args, **kws, device=0)
+    g1 = mcalf_b200.als_fitter(*args, **kws, device=1)
+    assert torch.cuda.current_device() == 0
+    U = np.random.default_rng(3).random((5000, g0.ndim))
+    ref = g0.lnlhood_batch(U, unit_cube=True)
+    assert np.array_equal(g1.lnlhood_batch(U, unit_cube=True), ref)                  # host path on device 1
+    assert torch.cuda.current_device() == 0
+    out = g1.lnlhood_batch(torch.from_numpy(U).to("cuda:1"), unit_cube=True)         # device path: cuda:1's current stream
+    torch.cuda.synchronize(1)
+    assert out.device.index == 1 and np.array_equal(out.cpu().numpy(), ref)
+    assert torch.cuda.current_device() == 0
+    with pytest.raises(ValueError):
+        g1.lnlhood_batch(torch.from_numpy(U).to("cuda:0"))                           # a tensor of the wrong device is refused
+    assert np.array_equal(g1.prior_transform_batch(U[:9]), g0.prior_transform_batch(U[:9]))
+    assert torch.cuda.current_device() == 0

@@ -318,6 +318,13 @@ def test_bench_size_batch_fp32_vs_fp64_kernel():
     assert np.array_equal(g.lnlhood_batch(U[pick], unit_cube=True), logl[pick])    # batch composition is irrelevant
     st = g.stats()
     assert st["samples_fp64"] == 4096            # nothing of the fp32 batch was silently re-routed
+    # ... and 64 of them directly against the oracle (numpy + scipy wofz), not only against the repo's own fp64 kernel
+    spot = pick[:64]
+    Pq = g.prior_transform_batch(U[spot])
+    ref_o = np.array([o.lnlhood_worker(p) for p in Pq])
+    worst_o = logl_close(logl[spot], ref_o, C)
+    assert np.allclose(ref[:64], ref_o, rtol=1e-10)
+    print("bench-size batch: worst relative logL difference fp32 kernel vs oracle %.2e (64 rows)" % worst_o)
     print("bench-size batch: worst relative logL difference fp32 vs fp64 kernel %.2e" % worst)
 
 
