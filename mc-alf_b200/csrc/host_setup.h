@@ -13,8 +13,6 @@ struct ChunkDesc {
     int start, len;
     float ds, inv_ds;     // max |delta| over the chunk (slightly widened), delta = rho - rho_s, and 1/ds
     double rho_s;
-    float d0, inv_dstep;  // linear model of the chunk's pixel grid: delta_k ~ d0 + k / inv_dstep
-    int kslack, pad_;     // max error of that model in pixels, rounded up, plus 2
 };
 
 constexpr int CHUNK_PIXELS = 256;
@@ -55,19 +53,6 @@ inline void build_chunks(const double *wave, int npix, double lam_ref, std::vect
         // widened a little so the classification bound also covers the dropped low part
         cd.ds = std::max(fabsf(dmin), fabsf(dmax)) * (1.0f + 1e-6f) + 1e-12f;
         cd.inv_ds = 1.0f / cd.ds;
-        cd.d0 = dhi[start];
-        cd.pad_ = 0;
-        const double step = len > 1 ? ((double)dhi[start + len - 1] - (double)dhi[start]) / (len - 1) : 0.0;
-        if (step != 0.0) {
-            cd.inv_dstep = (float)(1.0 / step);
-            double worst = 0.0;
-            for (int i = start; i < start + len; ++i)
-                worst = std::max(worst, fabs((double)(i - start) - ((double)dhi[i] - (double)cd.d0) / step));
-            cd.kslack = worst < 250.0 ? (int)ceil(worst) + 2 : CHUNK_PIXELS;
-        } else {
-            cd.inv_dstep = 0.0f;          // degenerate chunk: every row is a candidate
-            cd.kslack = CHUNK_PIXELS;
-        }
         chunks.push_back(cd);
         start += len;
     }
