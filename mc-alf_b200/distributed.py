@@ -136,7 +136,9 @@ class ShardedLikelihood:
             if hi > lo:
                 self.fitter.lnlhood_batch_peers(rows, [p + 8 * (base + lo) for p in peer.ptrs], unit_cube=unit_cube)
             peer.hdl.barrier(channel=half)          # on the current stream: every rank's stores have landed
-            return peer.buf[base:base + B]
+            # a private copy: the symmetric buffer half is written again two calls from now (the copy is stream-ordered
+            # before this rank arrives at the next barrier, which is what lets peers reuse the half safely)
+            return peer.buf[base:base + B].clone()
 
         self.gather_used = "nccl" if on_gpu else "collective"
         mine = torch.full((per,), float("nan"), dtype=torch.float64, device=dev)
