@@ -26,6 +26,20 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+// Shared-memory loads through an explicit 32-bit shared-window address (one register, computed once): in the hot
+// per-line loop the compiler otherwise re-derives the window base and the array offset for every access.
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float4 lds128(unsigned a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float lds32(unsigned a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+
 // one sample's results: local buffers, and the peers' gather buffers when the batch is one shard of a global one
 __device__ __forceinline__ void store_results(const BatchArgs &Bt, long long b, double logl, double chi2) {
     if (Bt.logl_out) Bt.logl_out[b] = logl;
@@ -364,7 +378,12 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             {
                 const float *fp = fslice + (lane < FF_NC ? lane : 0) * NS;
                 float cn = 0.0f;
-                for (int sidx = 0; sidx < NS; ++sidx) cn += fp[sidx];
+                if (NS == 8) {                   // the usual slot count: no remainder loop
+#pragma unroll
+                    for (int sidx = 0; sidx < 8; ++sidx) cn += fp[sidx];
+                } else {
+                    for (int sidx = 0; sidx < NS; ++sidx) cn += fp[sidx];
+                }
                 float C[FF_NC];
 #pragma unroll
                 for (int n = 0; n < FF_NC; ++n) C[n] = __shfl_sync(0xffffffffu, cn, n);
@@ -388,6 +407,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             // so it also serves the pixels just outside the boundary), or straddle both (both forms, per-pixel
             // select).  No pixel index is ever dynamic, so tau never leaves the registers.
             const int MW = P.mwords;
+            const unsigned lp_sa = smem_addr(S.lp), us_sa = smem_addr(uslice);
             for (int w = 0; w < MW; ++w) {
                 const unsigned cmw = S.cmask[c * MW + w];
                 for (unsigned m = S.nmask[c * MW + w]; m; m &= m - 1) {
@@ -395,13 +415,13 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const int t = (w << 5) + bit;
                     MCALF_CHK(t < h.nact && t < P.Lmax, 1);
                     MCALF_CHK(P.scratch_in_flux ? (uslice + t < S.flux + P.halo + cd.start + cd.len) : (t < P.Lmax), 3);
-                    const float4 *lp4 = reinterpret_cast<const float4 *>(&S.lp[t]);
-                    const float4 r0 = lp4[0], r1 = lp4[1], r2 = lp4[2];
+                    const unsigned la = lp_sa + (unsigned)t * (unsigned)sizeof(LineP);
+                    const float4 r0 = lds128(la), r1 = lds128(la + 16), r2 = lds128(la + 32);
                     LineP L;
                     L.A_hi = r0.x; L.a2 = r0.y; L.c1 = r0.z; L.ucm = r0.w;
                     L.cw0 = r1.x; L.cw1 = r1.y; L.cw2 = r1.z; L.cw3 = r1.w;
                     L.cw4 = r2.x; L.scut = r2.y; L.kappa = r2.z; L.a = r2.w;
-                    const float Uh = uslice[t];
+                    const float Uh = lds32(us_sa + 4u * (unsigned)t);
                     const F2 A2 = f2(L.A_hi), U2 = f2(Uh), a22 = f2(L.a2);
                     if (!((cmw >> bit) & 1u)) {
 #pragma unroll
@@ -411,7 +431,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                         }
                         continue;
                     }
-                    L.A_lo = lp4[3].x;
+                    L.A_lo = lds32(la + 48);
                     float Uh64, Ul;
                     split2(S.A64[t] * (cd.rho_s - S.rc64[t]), Uh64, Ul);      // Uh64 == Uh
                     const float2 *dl2 = P.dlo2 + cd.start + lane;
