@@ -58,6 +58,11 @@ CANON_EVAL = 5.0
 CANON_CORE, CANON_WING = 242.0, 36.0
 
 
+KIND_TEXT = {"reference": "the unmodified reference (mcalf.routines.hires_fitter.als_fitter.lnlhood_worker, numpy + scipy.special.wofz; "
+                          "astropy / linetools stood in by oracle/refshim.py)",
+             "port": "oracle port (numpy + scipy.special.wofz)"}
+
+
 def cfg4_spectrum():
     from mcalf_b200.workloads import config_kwargs    # input generation only
     return config_kwargs(4, GOLDEN)
@@ -127,13 +132,32 @@ class ClockSampler:
 # CPU legs (oracle port; the only place bench.py executes oracle/ code as a workload)
 # ---------------------------------------------------------------------------------------------
 _CPU_FITTER = None
+_CPU_KIND = None
 
 
 def _cpu_init():
-    global _CPU_FITTER
-    from oracle import mcalf_oracle as orc
+    """One fitter per worker: the UNMODIFIED reference (baseline/_ref or /root/reference, imported through
+    oracle/refshim.py, which only stands in for astropy / linetools) when it is there, else the oracle port."""
+    global _CPU_FITTER, _CPU_KIND
     spec, kw = cfg4_spectrum()
-    _CPU_FITTER = orc.OracleFitter(spec, **kw)
+    try:
+        from oracle import refshim
+        if not refshim.available():
+            raise ImportError("no reference tree")
+        hf = refshim.install()
+        fd, path = tempfile.mkstemp(suffix=".txt")
+        with os.fdopen(fd, "w") as fh:                     # the reference reads an ASCII table with a header line
+            fh.write("# Wave Flux Err\n")
+            np.savetxt(fh, np.column_stack(spec), fmt="%.17g")
+        _CPU_FITTER = hf.als_fitter(path, [list(r) for r in kw["fitrange"]], kw["fitlines"], list(kw["ncomp"]),
+                                    nfill=kw.get("nfill", 0), specres=list(kw["specres"]), contval=list(kw["contval"]),
+                                    Nrange=list(kw["Nrange"]), brange=list(kw["brange"]))
+        os.unlink(path)
+        _CPU_KIND = "reference"
+    except Exception:                                      # noqa: BLE001 -- any import / construction problem: use the port
+        from oracle import mcalf_oracle as orc
+        _CPU_FITTER = orc.OracleFitter(spec, **kw)
+        _CPU_KIND = "port"
 
 
 def _cpu_eval(U):
@@ -141,11 +165,17 @@ def _cpu_eval(U):
     return [f.lnlhood_worker(f._scale_cube_pc(u)) for u in U]
 
 
+def _cpu_kind(_):
+    return _CPU_KIND
+
+
 def cpu_pool():
     import multiprocessing as mp
     cores = len(os.sched_getaffinity(0))
     pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
     pool.map(_cpu_eval, [np.zeros((0, 63))] * cores)   # every worker builds its fitter outside the timed region
+    kinds = set(pool.map(_cpu_kind, range(4 * cores)))
+    pool.kind = "reference" if kinds == {"reference"} else "port"
     return pool, cores
 
 
@@ -172,15 +202,16 @@ def run_reference(args):
     for _ in range(args.warmup):
         cpu_time(pool, cores, U[:cores])
     t = sum(cpu_time(pool, cores, U) for _ in range(args.steps))
+    kind = pool.kind
     pool.close()
     v = n * args.steps / t
-    sample = "%d prior-draw parameter vectors of the cfg-4 workload per step" % n
+    sample = "%d prior-draw parameter vectors of the cfg-4 workload per step, %s" % (n, KIND_TEXT[pool.kind])
     emit({
         "metric": METRIC, "value": v, "unit": UNIT, "impl": "reference", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch_per_step": n},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": pool.kind, "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })
@@ -464,9 +495,8 @@ def run_ours(args):
             ncpu = max(cores * 32, 512)          # ~20 s of CPU work in total
             tcpu = cpu_time(pool, cores, Uh[:ncpu])
             pool.close()
-            cpu = {"value": ncpu / tcpu, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": "first %d parameter vectors of the timed batch, multiprocessing.Pool(%d), oracle port "
-                             "(numpy + scipy.special.wofz)" % (ncpu, cores)}
+            cpu = {"value": ncpu / tcpu, "unit": UNIT, "cores": cores, "kind": pool.kind,
+                   "sample": "first %d parameter vectors of the timed batch, multiprocessing.Pool(%d), %s" % (ncpu, cores, KIND_TEXT[pool.kind])}
         total = world * B * K
         line = {
             "metric": METRIC, "value": total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,

@@ -7,7 +7,8 @@ of the reference's own likelihood code (``als_fitter.__init__``, ``voigt_tau``, 
 ``convolve_model``, ``lnlhood_worker``, ``_scale_cube_pc``) then executes as shipped, with the real
 ``scipy.special.wofz``.
 
-Only usable where ``/root/reference`` exists (the build container).  It is used by
+Usable where ``/root/reference`` exists (the build container) or where the pip-installed copy
+``baseline/_ref`` travelled along (the GPU box; bench.py's CPU legs).  It is used by
 ``oracle/make_golden.py`` to generate the committed fixtures under ``tests/golden/`` and by
 ``tests/test_oracle_vs_reference.py`` (skipped when the reference tree is absent, e.g. on the GPU
 box).  The stand-ins are pinned by the reference's own mock spectra: ``Flux - N(0, 0.02; seed 42)``
@@ -21,7 +22,11 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MCALF_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# the reference tree in the build container, else the pip-installed copy that travels to the GPU box
+# (`pip install --no-deps --target baseline/_ref /root/reference`: git-ignored, never part of the history)
+_CANDIDATES = [os.environ.get("MCALF_REFERENCE_ROOT"), "/root/reference", os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isdir(os.path.join(c, "mcalf"))), "/root/reference")
 
 # wrest [Angstrom], f, gamma [1/s].  CIV rows are pinned by the golden vectors; the others are
 # from memory of Morton (2003) and are UNVERIFIED (harmless: oracle and product share the table).
