@@ -455,20 +455,21 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             {
                 float *dst = S.flux + P.halo + cd.start + lane;
                 MCALF_CHK(P.halo + cd.start + cd.len <= P.halo + P.npix, 6);
+                F2 dep[PX2];
+#pragma unroll
+                for (int j = 0; j < PX2; ++j) dep[j] = depth32_2(tau[j]);
                 if (cd.len == CHUNK_PIXELS) {
 #pragma unroll
                     for (int j = 0; j < PX2; ++j) {
-                        const F2 dep = depth32_2(tau[j]);
-                        dst[64 * j] = dep.x;
-                        dst[64 * j + 32] = dep.y;
+                        dst[64 * j] = dep[j].x;
+                        dst[64 * j + 32] = dep[j].y;
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < PX2; ++j) {
                         const int k = 2 * j * 32 + lane;
-                        const F2 dep = depth32_2(tau[j]);
-                        if (k < cd.len) dst[64 * j] = dep.x;
-                        if (k + 32 < cd.len) dst[64 * j + 32] = dep.y;
+                        if (k < cd.len) dst[64 * j] = dep[j].x;
+                        if (k + 32 < cd.len) dst[64 * j + 32] = dep[j].y;
                     }
                 }
             }
@@ -508,6 +509,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             MCALF_CHK(g < P.npix4 / 4, 9);
             float4 xl = xin[0];
             float o_0 = 0.f, o_1 = 0.f, o_2 = 0.f, o_3 = 0.f;
+#pragma unroll 2                 // (more unrolling costs more in instruction-cache misses on short spectra than it saves)
             for (int mb = 0; mb < nb; ++mb) {
                 const float4 xh = xin[mb + 1];
                 const float4 gg = gin[mb];
