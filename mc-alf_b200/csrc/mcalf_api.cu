@@ -634,6 +634,21 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
         P.scratch_in_flux = minlen >= (FF_NC_HOST * P.nslots + 1) + P.Lmax + 32 ? 1 : 0;   // + the bank skew
     }
 
+    // periodic halo of the depth buffer (astropy boundary='wrap', hires_fitter.py:463-464): cell H - 1 - j holds pixel
+    // (npix - 1 - j) mod npix, cell H + npix + j holds pixel j mod npix
+    std::vector<int> halo_src;
+    {
+        const int H = P.halo, tail = H + 8 + (P.npix4 - npix);
+        for (int cell = 0; cell < H; ++cell) {
+            const int j = H - 1 - cell;
+            int src = (npix - 1 - j) % npix;
+            if (src < 0) src += npix;
+            halo_src.push_back(src);
+        }
+        for (int j = 0; j < tail; ++j) halo_src.push_back(j % npix);
+        P.nhalo = (int)halo_src.size();
+    }
+
     std::vector<double> lw(p->line_wrest, p->line_wrest + p->nlines), lf(p->line_f, p->line_f + p->nlines),
         lg(p->line_gamma, p->line_gamma + p->nlines);
     lw.push_back(p->fill_wrest);
@@ -649,7 +664,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     build_pair_table(chunks, dlo, pl);
     static_assert(sizeof(PairF) == sizeof(float2), "pair table layout");
 #define UPF2(vec, field) { const PairF *tmp_ = nullptr; if ((rc = upload(c, vec, &tmp_)) != MCALF_OK) return rc; P.field = reinterpret_cast<const float2 *>(tmp_); }
-    UPF2(ph, dhi2) UPF2(pl, dlo2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(wave, wave) UP(obj, obj) UP(w, w)
+    UPF2(ph, dhi2) UPF2(pl, dlo2) UPF4(obj_hi, obj_hi4) UPF4(obj_lo, obj_lo4) UPF4(w32, w4) UP(chunks, chunks) UP(halo_src, halo_src) UP(wave, wave) UP(obj, obj) UP(w, w)
     UP(obj_raw, obj_raw) UP(isig, isig) UP(lw, line_wrest) UP(lf, line_f) UP(lg, line_gamma) UP(blo, blo) UP(bhi, bhi)
 #undef UP
 #undef UPF4

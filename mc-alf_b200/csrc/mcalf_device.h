@@ -26,7 +26,7 @@ struct DevProblem {
     int cslot_w, cslot_lw, nslots, vwarps; // lanes per chunk group (power of two), its log2, slots = vwarps * 32 / cslot_w
     float eps_cull, eps_far;
     SmemLayout lay;
-    int pad3_;
+    int nhalo;                          // halo cells: `halo` before pixel 0, the rest after the last pixel
     double fixed_specres, fixed_cont, velstep, lam_ref;
     double logC, asym_t5, asym_t4, a_max;
     double chi2_add;                    // +inf when a zero-error pixel makes the reference's chi2 infinite, else 0
@@ -35,6 +35,7 @@ struct DevProblem {
     const float4 *obj_hi4, *obj_lo4, *w4; // [npix4/4] flux as a two-float and weight 1/err^2, four pixels per element;
                                         // obj = w = 0 on dropped pixels and on the padding
     const ChunkDesc *chunks;            // [nchunks]
+    const int *halo_src;                // [nhalo] source pixel of every halo cell (periodic wrap)
     const double *wave, *obj, *w;       // [npix] fp64 copies for the check kernel (obj = w = 0 on dropped pixels)
     const double *obj_raw, *isig;       // [npix] untouched flux and 1/err for the Asymmlike counts
     const double *line_wrest, *line_f, *line_gamma;   // [nlines + 1], the last entry is the filler line

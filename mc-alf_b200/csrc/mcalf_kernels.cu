@@ -382,6 +382,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 #pragma unroll
                     for (int sidx = 0; sidx < 8; ++sidx) cn += fp[sidx];
                 } else {
+#pragma unroll 1
                     for (int sidx = 0; sidx < NS; ++sidx) cn += fp[sidx];
                 }
                 float C[FF_NC];
@@ -477,18 +478,16 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- periodic halo (astropy boundary='wrap' over the concatenated array, :463-464) ----
+        // ---- periodic halo (astropy boundary='wrap' over the concatenated array, :463-464): the cells before pixel 0 and
+        // after the last pixel copy the pixels the host listed (P.halo_src: no modulo arithmetic here) ----
         {
-            const int npix = P.npix, H = P.halo;
-            for (int j = tid; j < H; j += nthreads) {
-                int src = (npix - 1 - j) % npix;
-                if (src < 0) src += npix;
-                MCALF_CHK(src >= 0 && src < npix && H - 1 - j >= 0, 7);
-                S.flux[H - 1 - j] = S.flux[H + src];
+            const int H = P.halo, nh = P.nhalo;
+            MCALF_CHK(H + P.npix + (nh - H) <= 2 * P.halo + P.npix4 + 8, 7);
+            for (int j = tid; j < nh; j += nthreads) {
+                const int src = __ldg(P.halo_src + j);
+                MCALF_CHK(src >= 0 && src < P.npix, 7);
+                S.flux[j < H ? j : P.npix + j] = S.flux[H + src];       // j < H: cell j; else cell H + npix + (j - H)
             }
-            const int tail = H + 8 + (P.npix4 - npix);
-            MCALF_CHK(H + npix + tail <= 2 * P.halo + P.npix4 + 8, 7);
-            for (int j = tid; j < tail; j += nthreads) S.flux[H + npix + j] = S.flux[H + (j % npix)];
         }
         __syncthreads();
 

@@ -618,16 +618,24 @@ MCALF_HD F2 core_val2(const LineP &L, F2 u, F2 dh, F2 dl, float U_hi, float U_lo
 enum { PAIR_WING = 0, PAIR_CORE = 1, PAIR_BOTH = 2 };
 MCALF_HD int pair_kind(bool all_wing, bool all_tab) { return all_wing ? PAIR_WING : (all_tab ? PAIR_CORE : PAIR_BOTH); }
 
+// a row pair that straddles the table end and the core boundary (small b; rare): both forms, per-pixel select
+// (measured out of line to shrink the unrolled synthesis loop: the call costs more than the code size saves)
+MCALF_HD F2 straddle_pair_tau(F2 tau, F2 kh, F2 s, float scut, float cw0, float cw1, float cw2, float cw3, float cw4) {
+    LineP L;
+    L.cw0 = cw0; L.cw1 = cw1; L.cw2 = cw2; L.cw3 = cw3; L.cw4 = cw4;
+    F2 q;
+    const F2 sc = f2(fmaxf(s.x, scut), fmaxf(s.y, scut));
+    const F2 p = wing_val2(sc, L, q);
+    const F2 w = mul2(q, p);
+    return add2(tau, f2(s.x < scut ? kh.x : w.x, s.y < scut ? kh.y : w.y));
+}
+
 MCALF_HD F2 mixed_pair_tau(int kind, F2 tau, const LineP &L, F2 u, F2 s, F2 dh, F2 dl, float U_hi, float U_lo,
                            const G1Row *tab = nullptr) {
     if (kind == PAIR_WING) return wing_acc2(tau, s, L);
     const F2 kh = core_val2(L, u, dh, dl, U_hi, U_lo, tab);
     if (kind == PAIR_CORE) return add2(tau, kh);
-    F2 q;
-    const F2 sc = f2(fmaxf(s.x, L.scut), fmaxf(s.y, L.scut));
-    const F2 p = wing_val2(sc, L, q);
-    const F2 w = mul2(q, p);
-    return add2(tau, f2(s.x < L.scut ? kh.x : w.x, s.y < L.scut ? kh.y : w.y));
+    return straddle_pair_tau(tau, kh, s, L.scut, L.cw0, L.cw1, L.cw2, L.cw3, L.cw4);
 }
 
 // LSF geometry (hires_fitter.py:452-459): sigma in pixels and half-width n = ceil(3.0348 sigma).
