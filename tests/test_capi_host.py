@@ -119,3 +119,25 @@ def test_unknown_line_raises():
     g = mcalf_b200.als_fitter.__new__(mcalf_b200.als_fitter)
     with pytest.raises(ValueError):
         g._init_host(spec, [[6180, 6220]], ["XX 1234"], [1, 1])
+
+
+def test_checked_twin_and_new_entry_points(lib):
+    """The bounds-checked twin of the library is the same ABI (every symbol, same version) and says what it is; the
+    sharded entry point validates its arguments before touching a device."""
+    import importlib.util
+    from mcalf_b200 import capi
+    spec = importlib.util.spec_from_file_location("_b2", os.path.join(ROOT, "mc-alf_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    chk = ctypes.CDLL(mod.build(checked=True))
+    for name in capi.SIGNATURES:
+        assert getattr(chk, name) is not None
+    assert chk.mcalf_abi_version() == capi.ABI_VERSION == lib.mcalf_abi_version()
+    assert chk.mcalf_is_checked_build() == 1 and lib.mcalf_is_checked_build() == 0
+    arr = (ctypes.c_void_p * 2)(None, None)
+    assert lib.mcalf_loglike_batch_peers(None, None, 4, 4, capi.F_ON_DEVICE, None, arr, 0) == capi.E_INVALID      # npeers out of range
+    assert lib.mcalf_loglike_batch_peers(None, None, 4, 4, capi.F_ON_DEVICE, None, arr, 9) == capi.E_INVALID
+    assert lib.mcalf_loglike_batch_peers(None, None, 4, 4, capi.F_ON_DEVICE, None, arr, 2) == capi.E_INVALID      # null peer buffer
+    assert b"peer" in lib.mcalf_last_error()
+    assert lib.mcalf_loglike_batch_peers(None, None, 4, 4, 0, None, (ctypes.c_void_p * 1)(8), 1) == capi.E_INVALID  # host pointers refused
+    assert b"device pointers" in lib.mcalf_last_error()
