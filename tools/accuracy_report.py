@@ -24,4 +24,5 @@ for cfg, B in ((1, 512), (2, 384), (3, 96), (4, 96)):
                               logl_rel_fp64_max=float(rel64.max()), flux_err_fp32_max=float(fe32), flux_err_fp64_max=float(fe64),
                               logl_range=[float(ref.min()), float(ref.max())])
     print("cfg", cfg, out["cfg%d" % cfg])
-json.dump(out, open(os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "accuracy_r01.json"), "w"), indent=1)
+dst = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(GOLD), "..", "gpurun_out", "accuracy.json")
+json.dump(out, open(dst, "w"), indent=1)
