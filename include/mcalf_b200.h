@@ -91,8 +91,8 @@ typedef struct mcalf_stats {
     uint64_t evals_far;        /* ... in pairs folded into the chunk's far-field polynomial             */
     uint64_t evals_core_precise; /* ... of the core ones that took the two-float form (kappa > 8)          */
     uint64_t evals_core_straddle; /* ... of the core ones in row pairs that also needed the wing form (per-pixel select) */
-    double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events): device-pointer and small
-                                  host calls always, pipelined host slices only while collect_stats is on */
+    double last_kernel_ms;     /* device time of the last batch call's kernels (CUDA events): device-pointer calls always,
+                                  host-pointer calls only while collect_stats is on */
 } mcalf_stats_t;
 
 /* Build a context on CUDA device `device` (replaces als_fitter.__init__ state, :65-200). */

@@ -282,7 +282,7 @@ int enqueue(mcalf_ctx *c, Slot &s, cudaStream_t st, const double *d_params, long
     a.fallback_list = s.fallback;
     a.fallback_flag = fallback_flag;
     a.stats = c->collect_stats ? c->d_stats : nullptr;
-    const bool timed = c->collect_stats || &s == &c->dev_slot || &s == &c->zc_slot;   // last_kernel_ms; the pipelined slices skip the two records
+    const bool timed = c->collect_stats || &s == &c->dev_slot;   // last_kernel_ms; host-pointer calls skip the two records
     if (timed) CU(cudaEventRecord(s.k0, st));
     const int fp64_grid = (int)std::min<long long>(n, (long long)c->sm_count * 8);
     if (flags & MCALF_F_FP64) {

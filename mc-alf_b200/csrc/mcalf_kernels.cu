@@ -224,7 +224,10 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
 // DENSE: the 48-register build (CTAs of at most 256 threads, five per SM).  ptxas fits the kernel into 48 registers
 // with 20 bytes of spills and some rematerialisation: 4 % slower per warp, so it only pays where it seats a fifth CTA
 // (cfg 4: 40 instead of 32 warps per SM, +3 %; the host picks it, mcalf_api.cu:choose_launch).
-template <bool STATS, bool EXTRAS, bool DENSE>
+// ONE_EACH: the launch has one CTA per sample (small batches, the scalar callbacks): no work queue, the CTA takes
+// sample blockIdx.x and leaves -- two global atomics less on the latency path of a single call.  A separate
+// instantiation, because even these few instructions in the hand-over cost the big-batch kernel 1-2 % on short spectra.
+template <bool STATS, bool EXTRAS, bool DENSE, bool ONE_EACH>
 __global__ void __launch_bounds__(DENSE ? 256 : 1024, DENSE ? 5 : 1)
 mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ BatchArgs Bt) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -239,10 +242,13 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
     // per-thread statistics (only summed when Bt.stats != nullptr)
     unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0, st_both = 0;
 
-    for (;;) {
+    for (int round = 0;; ++round) {
         // ---- next sample (dynamic: the active-component count varies per sample) ----
         __syncthreads();
-        if (tid == 0) { S.misc[0] = (int)atomicAdd(Bt.work_counter, 1u); S.misc[3] = 0; }
+        if (tid == 0) {
+            S.misc[0] = ONE_EACH ? (round ? 0x7fffffff : (int)blockIdx.x) : (int)atomicAdd(Bt.work_counter, 1u);
+            S.misc[3] = 0;
+        }
         __syncthreads();
         const long long b = S.misc[0];
         if (b >= Bt.B) break;
@@ -768,27 +774,35 @@ static cudaError_t raise_smem_limit(K kernel, size_t optin, size_t *static_bytes
 }
 
 cudaError_t configure_kernels(size_t optin_bytes, size_t *fast_static_bytes) {
-    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, false, false>, optin_bytes, fast_static_bytes);
+    cudaError_t e = raise_smem_limit(mcalf_fast_kernel<false, false, false, false>, optin_bytes, fast_static_bytes);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<false, false, true>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, false, true, false>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<false, true, false>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, false, false, true>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
-    e = raise_smem_limit(mcalf_fast_kernel<true, true, false>, optin_bytes, nullptr);
+    e = raise_smem_limit(mcalf_fast_kernel<false, false, true, true>, optin_bytes, nullptr);
+    if (e != cudaSuccess) return e;
+    e = raise_smem_limit(mcalf_fast_kernel<false, true, false, false>, optin_bytes, nullptr);
+    if (e != cudaSuccess) return e;
+    e = raise_smem_limit(mcalf_fast_kernel<true, true, false, false>, optin_bytes, nullptr);
     if (e != cudaSuccess) return e;
     return raise_smem_limit(mcalf_fp64_kernel, optin_bytes, nullptr);
 }
 
 cudaError_t fast_occupancy(int threads, size_t smem, int dense, int *ctas_per_sm) {
-    if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, true>, threads, smem);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, false>, threads, smem);
+    if (dense) return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, true, false>, threads, smem);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, mcalf_fast_kernel<false, false, false, false>, threads, smem);
 }
 
 cudaError_t launch_fast(const DevProblem &P, const BatchArgs &Bt, int grid, int threads, size_t smem, int dense, cudaStream_t st) {
-    if (Bt.stats) mcalf_fast_kernel<true, true, false><<<grid, threads, smem, st>>>(P, Bt);
-    else if (Bt.flux_out != nullptr || P.asymmlike) mcalf_fast_kernel<false, true, false><<<grid, threads, smem, st>>>(P, Bt);
-    else if (dense && threads <= 256) mcalf_fast_kernel<false, false, true><<<grid, threads, smem, st>>>(P, Bt);
-    else mcalf_fast_kernel<false, false, false><<<grid, threads, smem, st>>>(P, Bt);
+    const bool one_each = (long long)grid >= Bt.B;          // one CTA per sample: no work queue
+    const bool d = dense && threads <= 256;
+    if (Bt.stats) mcalf_fast_kernel<true, true, false, false><<<grid, threads, smem, st>>>(P, Bt);
+    else if (Bt.flux_out != nullptr || P.asymmlike) mcalf_fast_kernel<false, true, false, false><<<grid, threads, smem, st>>>(P, Bt);
+    else if (one_each && d) mcalf_fast_kernel<false, false, true, true><<<grid, threads, smem, st>>>(P, Bt);
+    else if (one_each) mcalf_fast_kernel<false, false, false, true><<<grid, threads, smem, st>>>(P, Bt);
+    else if (d) mcalf_fast_kernel<false, false, true, false><<<grid, threads, smem, st>>>(P, Bt);
+    else mcalf_fast_kernel<false, false, false, false><<<grid, threads, smem, st>>>(P, Bt);
     return cudaGetLastError();
 }
 

@@ -41,7 +41,7 @@ PY
 # SASS of the shipped hot kernel
 cuobjdump -sass mc-alf_b200/libmcalf_b200.so > /tmp/all.sass
 # the instantiation the bench workload runs: <STATS=false, EXTRAS=false, DENSE=true> (48 registers, five CTAs per SM at cfg 4)
-L=$(grep -n "Function :" /tmp/all.sass | grep "ILb0ELb0ELb1E" | cut -d: -f1); N=$(grep -n "Function :" /tmp/all.sass | awk -F: -v l=$L '$1>l{print $1; exit}')
+L=$(grep -n "Function :" /tmp/all.sass | grep "ILb0ELb0ELb1ELb0E" | cut -d: -f1); N=$(grep -n "Function :" /tmp/all.sass | awk -F: -v l=$L '$1>l{print $1; exit}')
 [ -z "$N" ] && N=$(wc -l < /tmp/all.sass)
 ( echo "SASS of mcalf_fast_kernel<STATS=false, EXTRAS=false, DENSE=true> (sm_100a) from mc-alf_b200/libmcalf_b200.so, cuobjdump -sass; opcode totals first"; 
   sed -n "${L},${N}p" /tmp/all.sass | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*([0-9a-f]+)\*\/\s+/\1 /; s/\s*\/\*.*$//' > /tmp/hot.sass
