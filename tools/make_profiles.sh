@@ -40,10 +40,10 @@ print(d)
 PY
 # SASS of the shipped hot kernel
 cuobjdump -sass mc-alf_b200/libmcalf_b200.so > /tmp/all.sass
-# the instantiation the bench workload runs: <STATS=false, EXTRAS=false, DENSE=true> (48 registers, five CTAs per SM at cfg 4)
+# the instantiation the bench workload runs: <STATS=false, EXTRAS=false, DENSE=true, ONE_EACH=false> (48 registers, five CTAs per SM at cfg 4)
 L=$(grep -n "Function :" /tmp/all.sass | grep "ILb0ELb0ELb1ELb0E" | cut -d: -f1); N=$(grep -n "Function :" /tmp/all.sass | awk -F: -v l=$L '$1>l{print $1; exit}')
 [ -z "$N" ] && N=$(wc -l < /tmp/all.sass)
-( echo "SASS of mcalf_fast_kernel<STATS=false, EXTRAS=false, DENSE=true> (sm_100a) from mc-alf_b200/libmcalf_b200.so, cuobjdump -sass; opcode totals first"; 
+( echo "SASS of mcalf_fast_kernel<STATS=false, EXTRAS=false, DENSE=true, ONE_EACH=false> (sm_100a) from mc-alf_b200/libmcalf_b200.so, cuobjdump -sass; opcode totals first"; 
   sed -n "${L},${N}p" /tmp/all.sass | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed -E 's/^\s+\/\*([0-9a-f]+)\*\/\s+/\1 /; s/\s*\/\*.*$//' > /tmp/hot.sass
   awk '{op=$2; if (op ~ /^@/) op=$3; sub(/\..*/,"",op); c[op]++} END{for(k in c) printf "%6d %s\n", c[k], k}' /tmp/hot.sass | sort -rn | head -40
   echo; cat /tmp/hot.sass ) > profiles/sass_fast_kernel_$rnd.txt
