@@ -553,7 +553,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     DevProblem &P = c->P;
     const int npix = p->npix;
     P.npix = npix;
-    P.npix4 = (npix + 3) & ~3;
+    P.npix4 = (npix + 7) & ~7;             // two float4 groups per stencil thread
     P.nlines = p->nlines;
     P.ncompmax = p->ncompmax;
     P.nfill = p->nfill;
@@ -638,7 +638,7 @@ int mcalf_create(const mcalf_problem_t *p, int device, mcalf_ctx **out) {
     // (npix - 1 - j) mod npix, cell H + npix + j holds pixel j mod npix
     std::vector<int> halo_src;
     {
-        const int H = P.halo, tail = H + 8 + (P.npix4 - npix);
+        const int H = P.halo, tail = H + 12 + (P.npix4 - npix);
         for (int cell = 0; cell < H; ++cell) {
             const int j = H - 1 - cell;
             int src = (npix - 1 - j) % npix;

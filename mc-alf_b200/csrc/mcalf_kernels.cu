@@ -34,6 +34,14 @@ __device__ __forceinline__ float4 lds128(unsigned a) {
     asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
     return v;
 }
+// One lane's fetch-and-increment on shared memory (atom.inc with a bound that is never reached).  For atomicAdd --
+// also for atom.shared.add written as PTX -- ptxas emits its warp-aggregation sequence (vote, leader election, two
+// population counts, a shuffle: nine more instructions) although the caller has already elected one lane.
+__device__ __forceinline__ int atoms_inc(unsigned a) {
+    int r;
+    asm volatile("atom.shared.inc.u32 %0, [%1], %2;" : "=r"(r) : "r"(a), "r"(0x7fffffff) : "memory");
+    return r;
+}
 __device__ __forceinline__ float lds32(unsigned a) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
@@ -173,7 +181,7 @@ struct FastSmem {
     unsigned *cmask;   // [nchunks][mwords]   bit t: the core of line t may reach chunk c
     float *farp;       // [nchunks][FF_NC * nslots + 1] partial far-field coefficients, [n][slot] within a chunk
     float *taps;       // [2*nmax4 + 8]
-    float *flux;       // [halo + npix4 + halo + 8]
+    float *flux;       // [halo + npix4 + halo + 12]
     double *red;       // [64]
     int *misc;         // [8]
     size_t bytes;
@@ -196,7 +204,7 @@ static SmemLayout make_layout(const DevProblem &P) {
     L.taps = take(sizeof(float) * (2 * P.nmax4 + 8));
     L.red = take(sizeof(double) * 64);
     L.misc = take(sizeof(int) * 8);
-    L.flux = take(sizeof(float) * (2 * P.halo + P.npix4 + 8));
+    L.flux = take(sizeof(float) * (2 * P.halo + P.npix4 + 12));
     L.bytes = (int)o;
     return L;
 }
@@ -358,7 +366,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         // that sees only far lines, and the CTA's warps must meet at the barrier below
         for (;;) {
             int c = 0;
-            if (lane == 0) c = atomicAdd(&S.misc[3], 1);
+            if (lane == 0) c = atoms_inc(smem_addr(&S.misc[3]));
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
             MCALF_CHK(c >= 0 && c < P.nchunks, 13);
@@ -488,7 +496,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         // after the last pixel copy the pixels the host listed (P.halo_src: no modulo arithmetic here) ----
         {
             const int H = P.halo, nh = P.nhalo;
-            MCALF_CHK(H + P.npix + (nh - H) <= 2 * P.halo + P.npix4 + 8, 7);
+            MCALF_CHK(H + P.npix + (nh - H) <= 2 * P.halo + P.npix4 + 12, 7);
             for (int j = tid; j < nh; j += nthreads) {
                 const int src = __ldg(P.halo_src + j);
                 MCALF_CHK(src >= 0 && src < P.npix, 7);
@@ -502,45 +510,65 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         const float c_lo = (float)(h.cont - (double)c_hi);
         double acc = 0.0;
         int cnt5 = 0, cnt4 = 0;
-        const int ngroups = P.npix4 >> 2;
+        const int ngroups = P.npix4 >> 3;
         // taps G[m] are non-zero for m in [n4 - n, n4 + n]: blocks of four taps up to the one holding n4 + n
         const int nb = ((n4 + S.misc[6]) >> 2) + 1;
         for (int g = tid; g < ngroups; g += nthreads) {
-            const int o0 = g << 2;
+            const int o0 = g << 3;
             const float4 *xin = reinterpret_cast<const float4 *>(S.flux + (P.halo + o0 - n4));
             const float4 *gin = reinterpret_cast<const float4 *>(S.taps);
-            MCALF_CHK(P.halo + o0 - n4 >= 0 && P.halo + o0 - n4 + 4 * (nb + 1) <= 2 * P.halo + P.npix4 + 8, 8);
+            MCALF_CHK(P.halo + o0 - n4 >= 0 && P.halo + o0 - n4 + 4 * (nb + 2) <= 2 * P.halo + P.npix4 + 12, 8);
             MCALF_CHK(4 * nb <= 2 * P.nmax4 + 8, 4);
-            MCALF_CHK(g < P.npix4 / 4, 9);
-            float4 xl = xin[0];
-            float o_0 = 0.f, o_1 = 0.f, o_2 = 0.f, o_3 = 0.f;
-#pragma unroll 2                 // (more unrolling costs more in instruction-cache misses on short spectra than it saves)
+            MCALF_CHK(g < P.npix4 / 8, 9);
+            // eight outputs per thread: every block of four taps costs one window load and one tap load for 32 FMAs.
+            // Each output still adds its taps in order, so the result does not depend on the blocking.
+            float4 x0 = xin[0], x1 = xin[1];
+            float o_0 = 0.f, o_1 = 0.f, o_2 = 0.f, o_3 = 0.f, o_4 = 0.f, o_5 = 0.f, o_6 = 0.f, o_7 = 0.f;
+#pragma unroll 3                 // (the window rotates through three registers quads)
             for (int mb = 0; mb < nb; ++mb) {
-                const float4 xh = xin[mb + 1];
+                const float4 x2 = xin[mb + 2];
                 const float4 gg = gin[mb];
-                o_0 = fma32(gg.x, xl.x, o_0); o_1 = fma32(gg.x, xl.y, o_1); o_2 = fma32(gg.x, xl.z, o_2); o_3 = fma32(gg.x, xl.w, o_3);
-                o_0 = fma32(gg.y, xl.y, o_0); o_1 = fma32(gg.y, xl.z, o_1); o_2 = fma32(gg.y, xl.w, o_2); o_3 = fma32(gg.y, xh.x, o_3);
-                o_0 = fma32(gg.z, xl.z, o_0); o_1 = fma32(gg.z, xl.w, o_1); o_2 = fma32(gg.z, xh.x, o_2); o_3 = fma32(gg.z, xh.y, o_3);
-                o_0 = fma32(gg.w, xl.w, o_0); o_1 = fma32(gg.w, xh.x, o_1); o_2 = fma32(gg.w, xh.y, o_2); o_3 = fma32(gg.w, xh.z, o_3);
-                xl = xh;
+                o_0 = fma32(gg.x, x0.x, o_0); o_1 = fma32(gg.x, x0.y, o_1); o_2 = fma32(gg.x, x0.z, o_2); o_3 = fma32(gg.x, x0.w, o_3);
+                o_4 = fma32(gg.x, x1.x, o_4); o_5 = fma32(gg.x, x1.y, o_5); o_6 = fma32(gg.x, x1.z, o_6); o_7 = fma32(gg.x, x1.w, o_7);
+                o_0 = fma32(gg.y, x0.y, o_0); o_1 = fma32(gg.y, x0.z, o_1); o_2 = fma32(gg.y, x0.w, o_2); o_3 = fma32(gg.y, x1.x, o_3);
+                o_4 = fma32(gg.y, x1.y, o_4); o_5 = fma32(gg.y, x1.z, o_5); o_6 = fma32(gg.y, x1.w, o_6); o_7 = fma32(gg.y, x2.x, o_7);
+                o_0 = fma32(gg.z, x0.z, o_0); o_1 = fma32(gg.z, x0.w, o_1); o_2 = fma32(gg.z, x1.x, o_2); o_3 = fma32(gg.z, x1.y, o_3);
+                o_4 = fma32(gg.z, x1.z, o_4); o_5 = fma32(gg.z, x1.w, o_5); o_6 = fma32(gg.z, x2.x, o_6); o_7 = fma32(gg.z, x2.y, o_7);
+                o_0 = fma32(gg.w, x0.w, o_0); o_1 = fma32(gg.w, x1.x, o_1); o_2 = fma32(gg.w, x1.y, o_2); o_3 = fma32(gg.w, x1.z, o_3);
+                o_4 = fma32(gg.w, x1.w, o_4); o_5 = fma32(gg.w, x2.x, o_5); o_6 = fma32(gg.w, x2.y, o_6); o_7 = fma32(gg.w, x2.z, o_7);
+                x0 = x1;
+                x1 = x2;
             }
             // shared memory holds the absorption DEPTH 1 - exp(-tau); with unit-sum taps the convolved
             // model is cont * (1 - conv(depth)), so every rounding error scales with the depth, not with
             // the continuum (a coherent 1e-7 bias of the continuum level would move chi-square by
             // 2 w sum(resid) 1e-7 -- not small for one-signed residuals).  The pixel tables are padded
-            // to a multiple of four with w = 0, so no pixel needs a bounds test here.
-            const float4 oh = __ldg(P.obj_hi4 + g), ol = __ldg(P.obj_lo4 + g), ww = __ldg(P.w4 + g);
+            // to a multiple of eight with w = 0, so no pixel needs a bounds test here.
             const F2 mch = f2(-c_hi), mcl = f2(-c_lo), ch2 = f2(c_hi), cl2 = f2(c_lo);
-            const F2 oa = f2(o_0, o_1), ob = f2(o_2, o_3);
-            const F2 ra = add2(fma2(ch2, oa, add2(add2(f2(oh.x, oh.y), mch), add2(f2(ol.x, ol.y), mcl))), mul2(cl2, oa));
-            const F2 rb = add2(fma2(ch2, ob, add2(add2(f2(oh.z, oh.w), mch), add2(f2(ol.z, ol.w), mcl))), mul2(cl2, ob));
-            F2 p2 = mul2(mul2(f2(ww.x, ww.y), ra), ra);
-            p2 = fma2(mul2(f2(ww.z, ww.w), rb), rb, p2);
-            const float part = p2.x + p2.y;
+            float part;
+            {
+                const float4 oh = __ldg(P.obj_hi4 + 2 * g), ol = __ldg(P.obj_lo4 + 2 * g), ww = __ldg(P.w4 + 2 * g);
+                const F2 oa = f2(o_0, o_1), ob = f2(o_2, o_3);
+                const F2 ra = add2(fma2(ch2, oa, add2(add2(f2(oh.x, oh.y), mch), add2(f2(ol.x, ol.y), mcl))), mul2(cl2, oa));
+                const F2 rb = add2(fma2(ch2, ob, add2(add2(f2(oh.z, oh.w), mch), add2(f2(ol.z, ol.w), mcl))), mul2(cl2, ob));
+                F2 p2 = mul2(mul2(f2(ww.x, ww.y), ra), ra);
+                p2 = fma2(mul2(f2(ww.z, ww.w), rb), rb, p2);
+                part = p2.x + p2.y;
+            }
+            float part2;
+            {
+                const float4 oh = __ldg(P.obj_hi4 + 2 * g + 1), ol = __ldg(P.obj_lo4 + 2 * g + 1), ww = __ldg(P.w4 + 2 * g + 1);
+                const F2 oa = f2(o_4, o_5), ob = f2(o_6, o_7);
+                const F2 ra = add2(fma2(ch2, oa, add2(add2(f2(oh.x, oh.y), mch), add2(f2(ol.x, ol.y), mcl))), mul2(cl2, oa));
+                const F2 rb = add2(fma2(ch2, ob, add2(add2(f2(oh.z, oh.w), mch), add2(f2(ol.z, ol.w), mcl))), mul2(cl2, ob));
+                F2 p2 = mul2(mul2(f2(ww.x, ww.y), ra), ra);
+                p2 = fma2(mul2(f2(ww.z, ww.w), rb), rb, p2);
+                part2 = p2.x + p2.y;
+            }
             if (EXTRAS) {
-                const float out[4] = {o_0, o_1, o_2, o_3};
+                const float out[8] = {o_0, o_1, o_2, o_3, o_4, o_5, o_6, o_7};
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r = 0; r < 8; ++r) {
                     const int o = o0 + r;
                     if (o < P.npix) {
                         MCALF_CHK(b >= 0 && b < Bt.B, 11);
@@ -558,6 +586,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                 }
             }
             acc += (double)part;
+            acc += (double)part2;
         }
         acc = warp_sum(acc);
         if (EXTRAS && P.asymmlike) { cnt5 = warp_sum_int(cnt5); cnt4 = warp_sum_int(cnt4); }
