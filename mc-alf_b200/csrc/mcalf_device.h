@@ -11,7 +11,7 @@ namespace mcalf {
 
 // byte offsets of the fp32 kernel's dynamic shared-memory arrays (fast_smem_layout)
 struct SmemLayout {
-    int theta, A64, rc64, lp, uarr, nmask, cmask, farp, taps, flux, red, misc, bytes;
+    int theta, A64, rc64, lp, uarr, nmask, cmask, farp, taps, flux, red, misc, chk, bytes;
 };
 
 // Everything als_fitter.__init__ leaves behind (hires_fitter.py:65-200), in device form.

@@ -184,6 +184,7 @@ struct FastSmem {
     float *flux;       // [halo + npix4 + halo + 12]
     double *red;       // [64]
     int *misc;         // [8]
+    ChunkDesc *chk;    // [nchunks]  copy of the chunk descriptors (48-register build)
     size_t bytes;
 };
 
@@ -204,6 +205,7 @@ static SmemLayout make_layout(const DevProblem &P) {
     L.taps = take(sizeof(float) * (2 * P.nmax4 + 8));
     L.red = take(sizeof(double) * 64);
     L.misc = take(sizeof(int) * 8);
+    L.chk = take(sizeof(ChunkDesc) * P.nchunks);
     L.flux = take(sizeof(float) * (2 * P.halo + P.npix4 + 12));
     L.bytes = (int)o;
     return L;
@@ -223,6 +225,7 @@ __device__ __forceinline__ FastSmem carve(unsigned char *base, const DevProblem 
     s.flux = (float *)(base + P.lay.flux);
     s.red = (double *)(base + P.lay.red);
     s.misc = (int *)(base + P.lay.misc);
+    s.chk = (ChunkDesc *)(base + P.lay.chk);
     s.bytes = (size_t)P.lay.bytes;
     return s;
 }
@@ -246,6 +249,10 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
 
     __shared__ G1Row g1_smem[MCALF_G1_N];       // Taylor rows of H1 (line-core form), fixed address
     for (int i = tid; i < MCALF_G1_N; i += nthreads) g1_smem[i] = g1_tab_dev[i];
+    // the chunk descriptors: the 48-register build reads them from a copy in shared memory (a chunk's first instructions
+    // wait on them: +1 % at cfg 4); the 64-register build spills with the copy and keeps the global table (L1-resident)
+    if (DENSE) for (int i = tid; i < P.nchunks; i += nthreads) S.chk[i] = P.chunks[i];
+    const ChunkDesc *const chk = DENSE ? S.chk : P.chunks;
     if (blockIdx.x == 0 && tid == 0) { Bt.clear_counters[0] = 0u; Bt.clear_counters[1] = 0u; }   // for the slot's next launch
     // per-thread statistics (only summed when Bt.stats != nullptr)
     unsigned long long st_wing = 0, st_mixed = 0, st_core = 0, st_cull = 0, st_total = 0, st_far = 0, st_corep = 0, st_both = 0;
@@ -316,9 +323,9 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
                     const int c = cg + (lane & (W - 1));
                     const bool cact = c < P.nchunks;
                     const int cs = cact ? c : 0;
-                    const double rho_s = P.chunks[cs].rho_s;
-                    const float ds = P.chunks[cs].ds;
-                    float *fslice = P.scratch_in_flux ? S.flux + P.halo + P.chunks[cs].start + (cs & 31) : S.farp + (size_t)cs * fstride;   // skewed: lanes hit distinct banks
+                    const double rho_s = chk[cs].rho_s;
+                    const float ds = chk[cs].ds;
+                    float *fslice = P.scratch_in_flux ? S.flux + P.halo + chk[cs].start + (cs & 31) : S.farp + (size_t)cs * fstride;   // skewed: lanes hit distinct banks
                     float *uslice = P.scratch_in_flux ? fslice + fstride : S.uarr + (size_t)cs * P.Lmax;
                     F2 C[FF_NC / 2];               // coefficient pairs {C[2m], C[2m+1]}
 #pragma unroll
@@ -370,7 +377,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
             c = __shfl_sync(0xffffffffu, c, 0);
             if (c >= P.nchunks) break;
             MCALF_CHK(c >= 0 && c < P.nchunks, 13);
-            const ChunkDesc cd = P.chunks[c];
+            const ChunkDesc cd = chk[c];
             const int NS = P.nslots;
             MCALF_CHK(cd.start >= 0 && cd.len >= 1 && cd.len <= CHUNK_PIXELS && cd.start + cd.len <= P.npix, 13);
             const float *fslice = P.scratch_in_flux ? S.flux + P.halo + cd.start + (c & 31) : S.farp + (size_t)c * (FF_NC * NS + 1);
