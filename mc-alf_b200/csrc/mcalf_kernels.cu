@@ -512,7 +512,7 @@ mcalf_fast_kernel(const __grid_constant__ DevProblem P, const __grid_constant__ 
         }
         __syncthreads();
 
-        // ---- LSF stencil (4 outputs per thread, LDS.128) fused with continuum, residual, chi-square ----
+        // ---- LSF stencil (8 outputs per thread, LDS.128) fused with continuum, residual, chi-square ----
         const float c_hi = (float)h.cont;
         const float c_lo = (float)(h.cont - (double)c_hi);
         double acc = 0.0;
