@@ -45,3 +45,25 @@ def test_flop_model_matches_the_committed_opcode_histogram():
     n = np.full(B, 10.0)                                   # mean LSF half-width of the cfg-4 prior: 8..14 pixels
     approx = bench.model_flops(st, {"nchunks": 32}, B, npix, n) / B
     assert abs(approx / r["flop_per_logL_model"] - 1.0) < 0.05
+
+
+def test_committed_scaling_lines_are_one_consistent_set():
+    """profiles/bench_r02_{1,2,4,8}gpu.json: every line carries the contract's keys, the strong records evaluate the
+    same two global batches at every N, and their checksums (SHA-256 of the gathered logL bytes) are identical at
+    N = 1, 2, 4, 8 -- the G-invariance evidence the documents quote."""
+    lines = {n: json.load(open(os.path.join(ROOT, "profiles", "bench_r02_%dgpu.json" % n))) for n in (1, 2, 4, 8)}
+    sums = {}
+    for n, d in lines.items():
+        assert d["n_gpus"] == n and d["metric"] == "voigt_logL_evals_per_sec" and d["scaling"] == "weak"
+        for key in ("value", "ms_per_step", "e2e", "gpu_launches", "clocks", "roofline", "config", "dtype", "data"):
+            assert key in d, (n, key)
+        assert d["config"]["global_batch"] == n * d["config"]["batch_per_gpu"]
+        assert d["e2e"]["value"] <= d["value"] * 1.001 and d["e2e"]["h2d_bytes_per_step"] > 0
+        assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+        for s in d["strong"]:
+            assert s["bit_identical_to_single_gpu"] is True and s["batch_per_gpu"] * n >= s["global_batch"]
+            sums.setdefault(s["global_batch"], set()).add(s["global_checksum"])
+    assert set(sums) == {16384, 262144} and all(len(v) == 1 for v in sums.values()), sums
+    # weak scaling of the committed set: no N loses more than 3 % per GPU against N = 1
+    for n in (2, 4, 8):
+        assert lines[n]["value"] >= 0.97 * n * lines[1]["value"]
